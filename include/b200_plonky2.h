@@ -1,0 +1,134 @@
+/* libb200plonky2 -- C ABI of the B200-native plonky2 prover backend.
+ *
+ * Drop-in boundary: the Rust circuit code (CircuitBuilder, gadgets, witness generators)
+ * stays untouched; a patched plonky2::plonk::prover::prove() hands the FILLED WIRE MATRIX plus handles to the
+ * preprocessed circuit data across this ABI and gets plonky2's binary proof bytes back.
+ *
+ * Reference call sites each entry point replaces (paths relative to the reference tree):
+ *   b200_circuit_upload  <- CircuitBuilder::build::<C>()   near_bft_finality/src/prove_crypto/ed25519.rs:33,75,
+ *                           recursion.rs:94, sha256.rs:78, prove_block_data/keys_stakes.rs:243, primitives.rs:105,155,340
+ *                           (the constants/sigmas PolynomialBatch + circuit digest part of build(); gate placement,
+ *                           copy constraints and generator indexing stay in Rust)
+ *   b200_prove           <- CircuitData::prove(pw)          ed25519.rs:60,100, recursion.rs:95, sha256.rs:82,
+ *                           keys_stakes.rs:244, primitives.rs:108,158,343  (everything after generate_partial_witness)
+ *   b200_proof wire fmt  <- ProofWithPublicInputs::to_bytes near_bft_finality/src/prove_block_data/signatures.rs:225,
+ *                           src/bin/prove_block.rs:351
+ *   b200_ntt_batch / b200_lde_commit / b200_poseidon_merkle : the prover's inner loops exposed for benchmarking
+ *                           (upstream plonky2_field::fft, PolynomialBatch::from_values, MerkleTree::new; not in tree)
+ *
+ * Conventions: every uint64_t field element is little-endian canonical (< p = 2^64-2^32+1).  Matrices are
+ * COLUMN-MAJOR: polynomial c occupies elements [c*n, (c+1)*n).  All pointers are caller-owned and borrowed for
+ * the duration of the call unless stated.  Functions return 0 on success or a negative b200_status; the message
+ * is available from b200_last_error().  Calls on one context are serialized by the caller (one context per
+ * host thread / CUDA stream); distinct contexts may be used concurrently.  The library never aborts and has no
+ * CPU fallback: without a CUDA device b200_ctx_create fails with B200_ERR_CUDA.
+ */
+#ifndef B200_PLONKY2_H
+#define B200_PLONKY2_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B200_OK = 0,
+    B200_ERR_BAD_ARG = -1,
+    B200_ERR_CUDA = -2,
+    B200_ERR_UNSATISFIED = -3,   /* witness does not satisfy the circuit (quotient not a polynomial) */
+    B200_ERR_OOM = -4,
+    B200_ERR_UNSUPPORTED = -5    /* e.g. unknown gate id, zero-knowledge blinding, lookups */
+} b200_status;
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_circuit b200_circuit;
+
+/* Mirrors plonky2 CommonCircuitData (fields as serialized in common_data.json, see
+ * near_bft_finality/proofs/random/CGZP.../common_data.json and gnark-plonky2-verifier/types/common_data.go:11-58). */
+typedef struct {
+    uint32_t num_wires;
+    uint32_t num_routed_wires;
+    uint32_t num_constants;          /* total constant columns incl. selector columns (common_data.num_constants) */
+    uint32_t num_challenges;
+    uint32_t degree_bits;
+    uint32_t rate_bits;
+    uint32_t cap_height;
+    uint32_t proof_of_work_bits;
+    uint32_t num_query_rounds;
+    uint32_t quotient_degree_factor;
+    uint32_t num_partial_products;
+    uint32_t num_gate_constraints;
+    uint32_t num_public_inputs;
+    uint32_t hasher;                 /* 0 = PoseidonGoldilocksConfig; 1 = PoseidonBN128GoldilocksConfig (not yet) */
+    uint32_t num_reduction_arity_bits;
+    uint32_t reduction_arity_bits[16];
+    uint32_t num_gates;
+    const char *const *gate_ids;     /* plonky2 Gate::id() strings, in common_data.gates order */
+    const uint32_t *selector_indices;/* [num_gates] */
+    uint32_t num_selector_groups;
+    const uint32_t *group_starts;    /* [num_selector_groups] */
+    const uint32_t *group_ends;      /* [num_selector_groups] */
+    const uint64_t *k_is;            /* [num_routed_wires] */
+} b200_common;
+
+/* ---- context ---- */
+int b200_ctx_create(int device, b200_ctx **out);
+void b200_ctx_destroy(b200_ctx *ctx);
+/* Use an existing CUDA stream (cudaStream_t cast to void*) for all work of this context; NULL = own stream. */
+int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
+int b200_ctx_synchronize(b200_ctx *ctx);
+const char *b200_last_error(const b200_ctx *ctx);      /* valid until the next call on ctx */
+void b200_free(void *p);                                /* frees buffers returned by the library */
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+uint64_t b200_kernel_launches(const b200_ctx *ctx);
+
+/* ---- circuit (build-side) ----
+ * constants_sigmas_values: [num_constants + num_routed_wires][n] column-major VALUES on the subgroup H (natural
+ * order), i.e. plonky2's constant polys followed by the sigma polys.  Computes the constants/sigmas LDE + Merkle
+ * cap on the GPU and keeps everything resident.  cap_out (optional): 2^cap_height * 4 u64.
+ * circuit_digest: 4 u64 (GL hasher), as computed by build(). */
+int b200_circuit_upload(b200_ctx *ctx, const b200_common *common, const uint64_t *constants_sigmas_values,
+                        const uint64_t circuit_digest[4], uint64_t *cap_out, b200_circuit **out);
+void b200_circuit_free(b200_circuit *c);
+
+/* ---- prove ----
+ * wires: [num_wires][n] column-major (the full witness), public_inputs: [num_public_inputs].
+ * pow_witness_hint: 0 = grind the minimum nonce (== reference with RAYON_NUM_THREADS=1); otherwise the value is
+ * checked (16 leading zero bits) and used, so that a proof of the multi-threaded reference can be reproduced.
+ * proof_bytes: malloc'd by the library (ProofWithPublicInputs::to_bytes layout), release with b200_free. */
+int b200_prove(b200_ctx *ctx, const b200_circuit *circuit, const uint64_t *wires, const uint64_t *public_inputs,
+               size_t n_public_inputs, uint64_t pow_witness_hint, uint8_t **proof_bytes, size_t *proof_len);
+/* Same, wires already resident in device memory (device pointer). */
+int b200_prove_dev(b200_ctx *ctx, const b200_circuit *circuit, const uint64_t *d_wires, const uint64_t *public_inputs,
+                   size_t n_public_inputs, uint64_t pow_witness_hint, uint8_t **proof_bytes, size_t *proof_len);
+
+/* ---- inner loops (host-buffer entry points; *_dev variants take device pointers and run asynchronously on
+ * the context stream) ---- */
+/* Forward (inverse=0) or inverse NTT of `cols` polynomials of 2^log_n points, natural order in and out, in place. */
+int b200_ntt_batch(b200_ctx *ctx, uint64_t *values, size_t cols, uint32_t log_n, int inverse);
+int b200_ntt_batch_dev(b200_ctx *ctx, uint64_t *d_values, size_t cols, uint32_t log_n, int inverse, uint64_t *d_scratch);
+/* PolynomialBatch::from_values: values [cols][n] -> coefficients (bit-reversed storage, internal), LDE
+ * [cols][n << rate_bits] (row index bit-reversed, coset shift 7) and the Merkle cap (2^cap_height x 4 u64).
+ * lde_out / coeffs_out may be NULL (host variant).  coeffs_out is in natural order. */
+int b200_lde_commit(b200_ctx *ctx, const uint64_t *values, size_t cols, uint32_t log_n, uint32_t rate_bits,
+                    uint32_t cap_height, uint64_t *cap_out, uint64_t *lde_out, uint64_t *coeffs_out);
+int b200_lde_commit_dev(b200_ctx *ctx, const uint64_t *d_values, size_t cols, uint32_t log_n, uint32_t rate_bits,
+                        uint32_t cap_height, uint64_t *d_coeffs_br, uint64_t *d_lde, uint64_t *d_digests);
+/* Merkle cap over L = 2^log_L leaves given column-major data [cols][L]; digests_out (optional, host variant):
+ * all levels, b200_merkle_num_u64(log_L, cap_height) u64, cap last. */
+int b200_poseidon_merkle(b200_ctx *ctx, const uint64_t *data, size_t cols, uint32_t log_L, uint32_t cap_height,
+                         uint64_t *cap_out, uint64_t *digests_out);
+int b200_poseidon_merkle_dev(b200_ctx *ctx, const uint64_t *d_data, size_t cols, uint32_t log_L, uint32_t cap_height,
+                             uint64_t *d_digests);
+size_t b200_merkle_num_u64(uint32_t log_L, uint32_t cap_height);
+/* One arity-2^arity_bits FRI fold of 2^log_len extension-field values (interleaved a,b; bit-reversed coset order)
+ * by beta; shift = coset shift of the layer (7^(arity^layer)).  out: 2^(log_len-arity_bits) ext values. */
+int b200_fri_fold(b200_ctx *ctx, const uint64_t *values, uint32_t log_len, uint32_t arity_bits, const uint64_t beta[2],
+                  uint64_t shift, uint64_t *out);
+/* Poseidon permutation of `count` independent 12-word states (self-test / throughput probe). */
+int b200_poseidon_permute(b200_ctx *ctx, uint64_t *states, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

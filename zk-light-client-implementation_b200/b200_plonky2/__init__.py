@@ -1,0 +1,119 @@
+"""ctypes binding of libb200plonky2.so (the C ABI in include/b200_plonky2.h) and a thin host-side mirror of the
+reference's plonky2 surface for the hot path (CircuitData.prove / verify-less; see circuit_data.py).
+
+The CUDA library is the only implementation: importing this package without the built .so, or creating a
+Context without a CUDA device, raises -- there is no CPU fallback.
+"""
+import ctypes, os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200plonky2.so")
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libb200plonky2 error {code}: {msg}")
+        self.code = code
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} not built: run zk-light-client-implementation_b200/build.sh "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    return ctypes.CDLL(_LIB_PATH)
+
+lib = _load()
+u64p = ctypes.POINTER(ctypes.c_uint64)
+c_void_p, c_size_t, c_int, c_u32, c_u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64
+
+class Common(ctypes.Structure):
+    _fields_ = [(n, c_u32) for n in (
+        "num_wires", "num_routed_wires", "num_constants", "num_challenges", "degree_bits", "rate_bits", "cap_height",
+        "proof_of_work_bits", "num_query_rounds", "quotient_degree_factor", "num_partial_products",
+        "num_gate_constraints", "num_public_inputs", "hasher", "num_reduction_arity_bits")] + [
+        ("reduction_arity_bits", c_u32 * 16), ("num_gates", c_u32),
+        ("gate_ids", ctypes.POINTER(ctypes.c_char_p)), ("selector_indices", ctypes.POINTER(c_u32)),
+        ("num_selector_groups", c_u32), ("group_starts", ctypes.POINTER(c_u32)), ("group_ends", ctypes.POINTER(c_u32)),
+        ("k_is", u64p)]
+
+def _sig(name, restype, *argtypes):
+    f = getattr(lib, name); f.restype = restype; f.argtypes = list(argtypes); return f
+
+_sig("b200_ctx_create", c_int, c_int, ctypes.POINTER(c_void_p))
+_sig("b200_ctx_destroy", None, c_void_p)
+_sig("b200_ctx_set_stream", c_int, c_void_p, c_void_p)
+_sig("b200_ctx_synchronize", c_int, c_void_p)
+_sig("b200_last_error", ctypes.c_char_p, c_void_p)
+_sig("b200_free", None, c_void_p)
+_sig("b200_kernel_launches", c_u64, c_void_p)
+_sig("b200_merkle_num_u64", c_size_t, c_u32, c_u32)
+_sig("b200_ntt_batch", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_int)
+_sig("b200_ntt_batch_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_int, c_void_p)
+_sig("b200_lde_commit", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_u32, c_void_p, c_void_p, c_void_p)
+_sig("b200_lde_commit_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_u32, c_void_p, c_void_p, c_void_p)
+_sig("b200_poseidon_merkle", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p, c_void_p)
+_sig("b200_poseidon_merkle_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p)
+_sig("b200_poseidon_permute", c_int, c_void_p, c_void_p, c_size_t)
+
+EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_synchronize", "b200_last_error",
+           "b200_free", "b200_kernel_launches", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
+           "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
+           "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
+           "b200_poseidon_permute"]
+
+def _np(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a, a.ctypes.data_as(c_void_p)
+
+class Context:
+    """One per GPU / stream (b200_ctx)."""
+    def __init__(self, device=0):
+        h = c_void_p()
+        rc = lib.b200_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise B200Error(rc, "b200_ctx_create failed (no CUDA device?) -- no CPU fallback exists")
+        self.h = h
+    def close(self):
+        if self.h:
+            lib.b200_ctx_destroy(self.h); self.h = None
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+    def _chk(self, rc):
+        if rc != 0:
+            raise B200Error(rc, lib.b200_last_error(self.h).decode())
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(lib.b200_ctx_set_stream(self.h, c_void_p(cuda_stream_ptr)))
+    def synchronize(self):
+        self._chk(lib.b200_ctx_synchronize(self.h))
+    def kernel_launches(self):
+        return int(lib.b200_kernel_launches(self.h))
+
+    # ---- host-buffer entry points ----
+    def ntt_batch(self, values, log_n, inverse=False):
+        """values: [cols, 2^log_n] uint64 (natural order) -> transformed copy."""
+        a, p = _np(np.array(values, dtype=np.uint64, copy=True))
+        cols = a.shape[0]
+        self._chk(lib.b200_ntt_batch(self.h, p, cols, log_n, int(inverse)))
+        return a
+    def lde_commit(self, values, log_n, rate_bits=3, cap_height=4, want_lde=True, want_coeffs=True):
+        a, p = _np(values)
+        cols = a.shape[0]; n = 1 << log_n
+        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        lde = np.zeros((cols, n << rate_bits), dtype=np.uint64) if want_lde else None
+        co = np.zeros((cols, n), dtype=np.uint64) if want_coeffs else None
+        self._chk(lib.b200_lde_commit(self.h, p, cols, log_n, rate_bits, cap_height, cap.ctypes.data_as(c_void_p),
+                                      lde.ctypes.data_as(c_void_p) if want_lde else None,
+                                      co.ctypes.data_as(c_void_p) if want_coeffs else None))
+        return cap, lde, co
+    def poseidon_merkle(self, data, log_L, cap_height=4, want_digests=False):
+        a, p = _np(data)
+        cols = a.shape[0]
+        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        dg = np.zeros(lib.b200_merkle_num_u64(log_L, cap_height), dtype=np.uint64) if want_digests else None
+        self._chk(lib.b200_poseidon_merkle(self.h, p, cols, log_L, cap_height, cap.ctypes.data_as(c_void_p),
+                                           dg.ctypes.data_as(c_void_p) if want_digests else None))
+        return (cap, dg) if want_digests else cap
+    def poseidon_permute(self, states):
+        a, p = _np(np.array(states, dtype=np.uint64, copy=True))
+        self._chk(lib.b200_poseidon_permute(self.h, p, a.shape[0]))
+        return a

@@ -1,0 +1,48 @@
+// PolynomialBatch::from_values / from_coeffs on the GPU: iNTT -> coset LDE (rate 2^rate_bits, shift 7) ->
+// Poseidon leaf hashing -> Merkle cap.  (upstream plonky2::fri::oracle::PolynomialBatch; SURVEY.md 3.2 steps 3,6,9)
+#include "ctx.h"
+#include "poseidon.cuh"
+
+const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits) {
+    auto key = std::make_pair(log_n, rate_bits);
+    auto it = ctx->lde_scale.find(key);
+    if (it != ctx->lde_scale.end()) return it->second;
+    u64 *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t(8) << (log_n + rate_bits))));
+    lde_scale_table(p, log_n, rate_bits, GL_GEN, ctx->stream);
+    ctx->lde_scale[key] = p;
+    return p;
+}
+
+void commit_coeffs(b200_ctx *ctx, const u64 *d_coeffs_br, size_t cols, int log_n, int rate_bits, int cap_height,
+                   u64 *d_lde, u64 *d_digests) {
+    ntt_tables_ensure(ctx->tw, log_n + rate_bits, ctx->stream);
+    const u64 *scale = ctx_lde_scale(ctx, log_n, rate_bits);
+    size_t n = size_t(1) << log_n;
+    ntt_dif(ctx->tw, d_coeffs_br, n, true, d_lde, n << rate_bits, log_n, cols << rate_bits, rate_bits, scale, false, 1, ctx->stream);
+    merkle_leaves_colmajor(d_lde, cols, log_n + rate_bits, d_digests, ctx->stream);
+    merkle_build(d_digests, log_n + rate_bits, cap_height, ctx->stream);
+}
+
+void commit_values(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, int rate_bits, int cap_height,
+                   u64 *d_coeffs_br, u64 *d_lde, u64 *d_digests) {
+    ntt_tables_ensure(ctx->tw, log_n + rate_bits, ctx->stream);
+    size_t n = size_t(1) << log_n;
+    ntt_dif(ctx->tw, d_values, n, false, d_coeffs_br, n, log_n, cols, 0, nullptr, true, gl_inv((u64)n % GL_P), ctx->stream);
+    commit_coeffs(ctx, d_coeffs_br, cols, log_n, rate_bits, cap_height, d_lde, d_digests);
+}
+
+__global__ void k_permute_batch(u64 *st, size_t count) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = st[12 * i + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) st[12 * i + k] = s[k];
+}
+void poseidon_permute_batch(u64 *d_states, size_t count, cudaStream_t st) {
+    k_permute_batch<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_states, count);
+    LAUNCHED(1);
+}

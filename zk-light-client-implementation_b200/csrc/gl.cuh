@@ -1,0 +1,104 @@
+// Goldilocks field (p = 2^64 - 2^32 + 1) and its quadratic extension X^2 = 7, host + device.
+// Spec: plonky2_field::goldilocks_field (upstream, not vendored) as mirrored by
+// gnark-plonky2-verifier/goldilocks/base.go:33-39 and quadratic_extension.go:59-73.
+// All values stored in memory are canonical (< p).  Internally `gl_mul_nc` may return a
+// non-canonical representative in [0, 2^64); every *_nc result must go through gl_canon
+// before it is stored or compared.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+#define GL_P   0xFFFFFFFF00000001ULL
+#define GL_EPS 0x00000000FFFFFFFFULL
+#define GL_GEN 7ULL
+#define GL_ROOT32 1753635133440165772ULL   // primitive 2^32-th root of unity (base.go:37)
+
+#ifdef __CUDACC__
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_HD inline
+#endif
+
+GL_HD u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+
+// a, b canonical -> canonical
+GL_HD u64 gl_add(u64 a, u64 b) {
+    u64 s = a + b;
+    if (s < a) s += GL_EPS;            // wrapped past 2^64: 2^64 == EPS (mod p); result already < p
+    else if (s >= GL_P) s -= GL_P;
+    return s;
+}
+GL_HD u64 gl_sub(u64 a, u64 b) {
+    u64 d = a - b;
+    if (a < b) d -= GL_EPS;            // + p  ==  - EPS (mod 2^64)
+    return d;
+}
+GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
+
+GL_HD void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
+#ifdef __CUDA_ARCH__
+    lo = a * b; hi = __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128)a * b; lo = (u64)p; hi = (u64)(p >> 64);
+#endif
+}
+
+// (hi*2^64 + lo) mod p, result in [0, 2^64) (not necessarily canonical).
+// 2^64 == 2^32 - 1, 2^96 == -1 (mod p).
+GL_HD u64 gl_reduce128_nc(u64 lo, u64 hi) {
+    u64 hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
+    u64 t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= GL_EPS;
+    u64 t1 = hi_lo * GL_EPS;           // (hi_lo << 32) - hi_lo, fits in 64 bits
+    u64 r = t0 + t1;
+    if (r < t1) r += GL_EPS;
+    return r;
+}
+GL_HD u64 gl_mul_nc(u64 a, u64 b) { u64 lo, hi; gl_mul_wide(a, b, lo, hi); return gl_reduce128_nc(lo, hi); }
+GL_HD u64 gl_mul(u64 a, u64 b) { return gl_canon(gl_mul_nc(a, b)); }
+GL_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+
+GL_HD u64 gl_pow(u64 a, u64 e) {
+    u64 r = 1;
+    while (e) { if (e & 1) r = gl_mul(r, a); a = gl_mul(a, a); e >>= 1; }
+    return r;
+}
+GL_HD u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
+GL_HD u64 gl_root_of_unity(int n_log) {       // base.go:445-455
+    u64 r = GL_ROOT32;
+    for (int i = n_log; i < 32; i++) r = gl_mul(r, r);
+    return r;
+}
+GL_HD u32 bitrev32(u32 x, int bits) {
+#ifdef __CUDA_ARCH__
+    return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+    u32 r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r;
+#endif
+}
+
+// ---- quadratic extension ----
+struct gl2 { u64 a, b; };
+GL_HD gl2 gl2_make(u64 a, u64 b) { gl2 r; r.a = a; r.b = b; return r; }
+GL_HD gl2 gl2_add(gl2 x, gl2 y) { return gl2_make(gl_add(x.a, y.a), gl_add(x.b, y.b)); }
+GL_HD gl2 gl2_sub(gl2 x, gl2 y) { return gl2_make(gl_sub(x.a, y.a), gl_sub(x.b, y.b)); }
+GL_HD gl2 gl2_mul(gl2 x, gl2 y) {
+    u64 bb = gl_mul(x.b, y.b);
+    u64 w = gl_add(gl_add(gl_add(bb, bb), gl_add(bb, bb)), gl_add(gl_add(bb, bb), bb));   // 7*bb
+    return gl2_make(gl_add(gl_mul(x.a, y.a), w), gl_add(gl_mul(x.a, y.b), gl_mul(x.b, y.a)));
+}
+GL_HD gl2 gl2_scale(gl2 x, u64 s) { return gl2_make(gl_mul(x.a, s), gl_mul(x.b, s)); }
+GL_HD gl2 gl2_add_base(gl2 x, u64 s) { return gl2_make(gl_add(x.a, s), x.b); }
+GL_HD gl2 gl2_inv(gl2 x) {
+    u64 d = gl_inv(gl_sub(gl_mul(x.a, x.a), gl_mul(7, gl_mul(x.b, x.b))));
+    return gl2_make(gl_mul(x.a, d), gl_mul(gl_neg(x.b), d));
+}
+GL_HD gl2 gl2_pow(gl2 a, u64 e) {
+    gl2 r = gl2_make(1, 0);
+    while (e) { if (e & 1) r = gl2_mul(r, a); a = gl2_mul(a, a); e >>= 1; }
+    return r;
+}
+GL_HD bool gl2_eq(gl2 x, gl2 y) { return x.a == y.a && x.b == y.b; }
