@@ -1,0 +1,60 @@
+"""Synthetic circuits shaped like the reference's proofs (gate types, wire widths, row counts), built with the
+mini CircuitBuilder.  'sig' mirrors the ed25519 signature circuit (wide_ecc_config, u32 gate mix:
+crypto/plonky2_ed25519 + plonky2_sha512 + plonky2_u32 gates); 'rec' mirrors a recursive_proof circuit
+(standard_recursion_config, Poseidon-heavy: near_bft_finality/src/prove_crypto/recursion.rs)."""
+import numpy as np
+from . import circuit_builder as cb
+
+def _mix(total, weights):
+    w = np.array(weights, dtype=float); w /= w.sum()
+    cnt = np.floor(w * total).astype(int)
+    return [max(1, c) for c in cnt]
+
+def sig_circuit(degree_bits, seed=0, num_public_inputs=8):
+    """ed25519-sub-proof-shaped circuit: 234 wires, 2^degree_bits rows."""
+    cfg = cb.CircuitConfig.wide_ecc_config()
+    rng = np.random.default_rng(seed)
+    b = cb.CircuitBuilder(cfg)
+    pis = [int(x) for x in rng.integers(0, 1 << 32, size=num_public_inputs)]
+    b.register_public_inputs(pis)
+    budget = (1 << degree_bits) - b.num_rows - 8
+    assert budget > 40, "degree_bits too small for the sig-shaped mix"
+    c = _mix(budget, [40, 6, 6, 8, 5, 8, 6, 6, 2, 8, 3, 2])
+    cb.fill_u32_arithmetic(b, rng, c[0])
+    cb.fill_u32_add_many(b, rng, c[1], 2)
+    cb.fill_u32_add_many(b, rng, c[2], 5)
+    cb.fill_u32_subtraction(b, rng, c[3])
+    cb.fill_u32_range_check(b, rng, c[4], 8)
+    cb.fill_u32_interleave(b, rng, c[5])
+    cb.fill_uninterleave(b, rng, c[6], False)
+    cb.fill_uninterleave(b, rng, c[7], True)
+    cb.fill_comparison(b, rng, c[8])
+    r1 = cb.fill_arithmetic(b, rng, c[9])
+    cb.fill_base_sum(b, rng, c[10])
+    cs = rng.integers(0, 1 << 62, size=(c[11], 2), dtype=np.uint64)
+    rc = cb.fill_constant(b, cs)
+    # cross-row copy constraints: pairs of arithmetic rows share their first multiplicand via a constant row
+    k = min(len(rc), len(r1))
+    return b, (rc, r1, k)
+
+def rec_circuit(degree_bits, seed=0, num_public_inputs=4):
+    """recursive_proof-shaped circuit: 135 wires, Poseidon-dominated."""
+    cfg = cb.CircuitConfig.standard_recursion_config()
+    rng = np.random.default_rng(seed)
+    b = cb.CircuitBuilder(cfg)
+    pis = [int(x) for x in rng.integers(0, 1 << 32, size=num_public_inputs)]
+    b.register_public_inputs(pis)
+    budget = (1 << degree_bits) - b.num_rows - 4
+    assert budget > 12
+    c = _mix(budget, [55, 25, 10, 10])
+    cb.fill_poseidon_chain(b, rng, c[0])
+    cb.fill_arithmetic(b, rng, c[1])
+    cb.fill_base_sum(b, rng, c[2])
+    cb.fill_constant(b, rng.integers(0, 1 << 62, size=(c[3], 2), dtype=np.uint64))
+    return b, None
+
+def build(kind, degree_bits, seed=0):
+    b, _ = (sig_circuit if kind == "sig" else rec_circuit)(degree_bits, seed)
+    cd = b.build()
+    assert cd.common["degree_bits"] == degree_bits, (cd.common["degree_bits"], degree_bits)
+    return cd
