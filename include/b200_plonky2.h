@@ -81,6 +81,11 @@ const char *b200_last_error(const b200_ctx *ctx);      /* valid until the next c
 void b200_free(void *p);                                /* frees buffers returned by the library */
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t b200_kernel_launches(const b200_ctx *ctx);
+/* Phase timing: when enabled, CUDA events are recorded on the context stream around the prover's phases
+ * (lde, leaf_hash_wide = the dominant Poseidon leaf kernel, quotient, fri_combine, ...).  b200_ctx_timings
+ * synchronizes and returns a JSON object {"phase": [total_ms, count], ...} accumulated since the last call. */
+int b200_ctx_enable_timing(b200_ctx *ctx, int enable);
+const char *b200_ctx_timings(b200_ctx *ctx);
 
 /* ---- circuit (build-side) ----
  * constants_sigmas_values: [num_constants + num_routed_wires][n] column-major VALUES on the subgroup H (natural

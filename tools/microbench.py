@@ -23,7 +23,9 @@ def main():
     cols = int(sys.argv[2]) if len(sys.argv) > 2 else 234
     torch.cuda.set_device(0)
     ctx = bp.Context(0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     n = 1 << log_n; N = n << 3
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     vals = torch.randint(0, (1 << 62), (cols, n), dtype=torch.int64, device="cuda", generator=g)

@@ -46,6 +46,8 @@ _sig("b200_last_error", ctypes.c_char_p, c_void_p)
 _sig("b200_free", None, c_void_p)
 _sig("b200_kernel_launches", c_u64, c_void_p)
 _sig("b200_merkle_num_u64", c_size_t, c_u32, c_u32)
+_sig("b200_ctx_enable_timing", c_int, c_void_p, c_int)
+_sig("b200_ctx_timings", ctypes.c_char_p, c_void_p)
 _sig("b200_ntt_batch", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_int)
 _sig("b200_ntt_batch_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_int, c_void_p)
 _sig("b200_lde_commit", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_u32, c_void_p, c_void_p, c_void_p)
@@ -55,7 +57,7 @@ _sig("b200_poseidon_merkle_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u
 _sig("b200_poseidon_permute", c_int, c_void_p, c_void_p, c_size_t)
 
 EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_synchronize", "b200_last_error",
-           "b200_free", "b200_kernel_launches", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
+           "b200_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
            "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
            "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
            "b200_poseidon_permute"]
@@ -87,6 +89,11 @@ class Context:
         self._chk(lib.b200_ctx_synchronize(self.h))
     def kernel_launches(self):
         return int(lib.b200_kernel_launches(self.h))
+    def enable_timing(self, on=True):
+        self._chk(lib.b200_ctx_enable_timing(self.h, int(on)))
+    def timings(self):
+        import json
+        return json.loads(lib.b200_ctx_timings(self.h).decode())
 
     # ---- host-buffer entry points ----
     def ntt_batch(self, values, log_n, inverse=False):

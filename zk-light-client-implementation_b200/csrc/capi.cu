@@ -42,6 +42,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ntt_tables_free(ctx->tw);
     for (auto &kv : ctx->lde_scale) cudaFree(kv.second);
+    if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -66,6 +67,37 @@ int b200_ctx_synchronize(b200_ctx *ctx) {
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void b200_free(void *p) { free(p); }
 uint64_t b200_kernel_launches(const b200_ctx *) { return g_b200_launches; }
+
+int b200_ctx_enable_timing(b200_ctx *ctx, int enable) {
+    API_BEGIN(ctx)
+    ctx->timing = enable != 0;
+    return B200_OK;
+    API_END(ctx)
+}
+
+// JSON object {"phase": [total_ms, launches], ...} accumulated since the last call; clears the record.
+const char *b200_ctx_timings(b200_ctx *ctx) {
+    if (!ctx) return "{}";
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    for (auto &e : ctx->timing_events) {
+        float ms = 0; cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+        if (!acc.count(e.first)) order.push_back(e.first);
+        acc[e.first].first += ms; acc[e.first].second += 1;
+        cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+    }
+    ctx->timing_events.clear();
+    std::string j = "{";
+    for (size_t i = 0; i < order.size(); i++) {
+        char buf[160]; snprintf(buf, sizeof buf, "%s\"%s\": [%.4f, %d]", i ? ", " : "", order[i].c_str(), acc[order[i]].first, acc[order[i]].second);
+        j += buf;
+    }
+    j += "}";
+    ctx->timing_json = j;
+    return ctx->timing_json.c_str();
+}
 size_t b200_merkle_num_u64(uint32_t log_L, uint32_t cap_height) { return merkle_num_u64((int)log_L, (int)cap_height); }
 
 // ---------------- NTT ----------------

@@ -5,6 +5,8 @@
 #include <string>
 #include <exception>
 #include <new>
+#include <memory>
+#include <vector>
 
 struct ApiErr { int code; std::string msg; };
 
@@ -15,6 +17,23 @@ struct b200_ctx {
     NttTables tw;
     std::map<std::pair<int, int>, u64 *> lde_scale;   // (log_n, rate_bits) -> coset scaling table [2^rate_bits][n] (br storage)
     std::string err;
+    void *arena = nullptr; size_t arena_bytes = 0;   // grow-only scratch for b200_prove
+    u64 *tmp_q_big = nullptr;
+    // optional phase timing (b200_ctx_enable_timing): CUDA events on the context stream around prover phases
+    bool timing = false;
+    std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timing_events;
+    std::string timing_json;
+};
+struct PhaseTimer {     // RAII: records start/stop events for one named phase when timing is enabled
+    b200_ctx *ctx; size_t idx; bool on;
+    PhaseTimer(b200_ctx *c, const char *name) : ctx(c), idx(0), on(c->timing) {
+        if (!on) return;
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+        idx = c->timing_events.size();
+        c->timing_events.push_back({name, {a, b}});
+    }
+    ~PhaseTimer() { if (on) cudaEventRecord(ctx->timing_events[idx].second.second, ctx->stream); }
 };
 
 // coset scaling table for the LDE, cached per size

@@ -10,6 +10,7 @@
 
 typedef uint64_t u64;
 typedef uint32_t u32;
+typedef uint8_t u8;
 
 #define GL_P   0xFFFFFFFF00000001ULL
 #define GL_EPS 0x00000000FFFFFFFFULL

@@ -1,0 +1,367 @@
+// Prover kernels: permutation partial products / Z, quotient evaluation on the 8n coset, polynomial openings,
+// FRI batching + folding, proof-of-work grinding.  (loops C and D of section 8.)
+// Replaces upstream plonky2 plonk/prover.rs::{wires_permutation_partial_products_and_zs, compute_quotient_polys},
+// plonk/vanishing_poly.rs::eval_vanishing_poly_base_batch, fri/oracle.rs::prove_openings, fri/prover.rs.
+#include "plonk.cuh"
+
+// =====================================================================================================
+// 1. partial products and Z
+// =====================================================================================================
+// per row i and challenge c: q_k = prod_{j in chunk k} (w_j + beta*k_j*x + gamma) / (w_j + beta*sigma_j + gamma)
+// chunkq layout: [c][k][i] ; rowprod: [c][i]
+__global__ void __launch_bounds__(128) k_chunk_quotients(const u64 *__restrict__ wires, const u64 *__restrict__ sigmas, const u64 *__restrict__ kis,
+                                                         const u64 *__restrict__ tw, int log_n, u32 R, u32 npp, u32 qdf, u32 nch,
+                                                         u64 b0, u64 g0, u64 b1, u64 g1, u64 *__restrict__ chunkq, u64 *__restrict__ rowprod) {
+    size_t n = size_t(1) << log_n;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // x = w_n^i from the twiddle table: tw[h + j] = w_{2h}^j, 2h = n
+    u64 x;
+    { size_t h = n >> 1; x = (i < h) ? tw[h + i] : gl_neg(tw[h + (i - h)]); if (n == 1) x = 1; }
+    for (u32 c = 0; c < nch; c++) {
+        u64 beta = c ? b1 : b0, gamma = c ? g1 : g0;
+        u64 nums[16], dens[16];
+        for (u32 k = 0; k <= npp; k++) {
+            u64 num = 1, den = 1;
+            for (u32 j = k * qdf; j < (k + 1) * qdf && j < R; j++) {
+                u64 wv = wires[(size_t)j * n + i];
+                u64 t = gl_add(wv, gamma);
+                num = gl_mul(num, gl_add(t, gl_mul(beta, gl_mul(kis[j], x))));
+                den = gl_mul(den, gl_add(t, gl_mul(beta, sigmas[(size_t)j * n + i])));
+            }
+            nums[k] = num; dens[k] = den;
+        }
+        // batch inversion of dens[0..npp]
+        u64 pref[16]; u64 acc = 1;
+        for (u32 k = 0; k <= npp; k++) { pref[k] = acc; acc = gl_mul(acc, dens[k]); }
+        u64 inv = gl_inv(acc);
+        u64 rp = 1;
+        for (int k = (int)npp; k >= 0; k--) {
+            u64 dinv = gl_mul(inv, pref[k]);
+            inv = gl_mul(inv, dens[k]);
+            u64 q = gl_mul(nums[k], dinv);
+            chunkq[((size_t)c * (npp + 1) + k) * n + i] = q;
+            rp = gl_mul(rp, q);
+        }
+        rowprod[(size_t)c * n + i] = rp;
+    }
+}
+
+// exclusive multiplicative scan over rows, 1024 elements per block
+#define SCAN_T 256
+#define SCAN_E 4
+__global__ void __launch_bounds__(SCAN_T) k_scan_local(const u64 *__restrict__ in, u64 *__restrict__ excl, u64 *__restrict__ block_tot, size_t n) {
+    __shared__ u64 sh[SCAN_T];
+    size_t c = blockIdx.y;
+    size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_E + threadIdx.x * SCAN_E;
+    u64 v[SCAN_E]; u64 loc = 1;
+#pragma unroll
+    for (int e = 0; e < SCAN_E; e++) { v[e] = (base + e < n) ? in[c * n + base + e] : 1; loc = gl_mul(loc, v[e]); }
+    sh[threadIdx.x] = loc;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over thread totals
+    for (int off = 1; off < SCAN_T; off <<= 1) {
+        u64 t = (threadIdx.x >= off) ? sh[threadIdx.x - off] : 1;
+        __syncthreads();
+        sh[threadIdx.x] = gl_mul(sh[threadIdx.x], t);
+        __syncthreads();
+    }
+    u64 pre = threadIdx.x ? sh[threadIdx.x - 1] : 1;
+#pragma unroll
+    for (int e = 0; e < SCAN_E; e++) { if (base + e < n) excl[c * n + base + e] = pre; pre = gl_mul(pre, v[e]); }
+    if (threadIdx.x == SCAN_T - 1) block_tot[c * gridDim.x + blockIdx.x] = sh[SCAN_T - 1];
+}
+__global__ void k_scan_blocks(u64 *block_tot, u32 nblocks, u64 *final_prod) {   // one thread per challenge (nblocks small)
+    u32 c = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    u64 acc = 1;
+    for (u32 b = 0; b < nblocks; b++) { u64 t = block_tot[c * nblocks + b]; block_tot[c * nblocks + b] = acc; acc = gl_mul(acc, t); }
+    final_prod[c] = acc;
+}
+// Z[i] = blockoff * excl[i]; pp_k[i] = Z[i] * prod_{j<=k} q_j[i]
+__global__ void __launch_bounds__(128) k_finish_zpp(const u64 *__restrict__ excl, const u64 *__restrict__ block_off, const u64 *__restrict__ chunkq,
+                                                    size_t n, u32 npp, u32 nch, u32 nblocks, u64 *__restrict__ zs_pp) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (u32 c = 0; c < nch; c++) {
+        u64 z = gl_mul(excl[(size_t)c * n + i], block_off[c * nblocks + i / (SCAN_T * SCAN_E)]);
+        zs_pp[(size_t)c * n + i] = z;
+        u64 acc = z;
+        for (u32 k = 0; k < npp; k++) {
+            acc = gl_mul(acc, chunkq[((size_t)c * (npp + 1) + k) * n + i]);
+            zs_pp[((size_t)nch + (size_t)c * npp + k) * n + i] = acc;
+        }
+    }
+}
+
+void launch_partial_products(const u64 *d_wires, const u64 *d_sigmas, const u64 *d_kis, int log_n, u32 R, u32 npp, u32 qdf,
+                             u32 nch, const u64 *betas, const u64 *gammas, const u64 *tw_fwd, u64 *d_zs_pp, u64 *d_scratch,
+                             u64 *d_final_prod, cudaStream_t st) {
+    size_t n = size_t(1) << log_n;
+    u64 *chunkq = d_scratch;                               // nch*(npp+1)*n
+    u64 *rowprod = chunkq + (size_t)nch * (npp + 1) * n;   // nch*n  (reused as excl)
+    u32 nblocks = (u32)((n + SCAN_T * SCAN_E - 1) / (SCAN_T * SCAN_E));
+    u64 *block_tot = rowprod + (size_t)nch * n;            // nch*nblocks
+    k_chunk_quotients<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_wires, d_sigmas, d_kis, tw_fwd, log_n, R, npp, qdf, nch,
+                                                                  betas[0], gammas[0], nch > 1 ? betas[1] : 0, nch > 1 ? gammas[1] : 0, chunkq, rowprod);
+    LAUNCHED(1);
+    k_scan_local<<<dim3(nblocks, nch), SCAN_T, 0, st>>>(rowprod, rowprod, block_tot, n);
+    LAUNCHED(1);
+    k_scan_blocks<<<nch, 32, 0, st>>>(block_tot, nblocks, d_final_prod);
+    LAUNCHED(1);
+    k_finish_zpp<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rowprod, block_tot, chunkq, n, npp, nch, nblocks, d_zs_pp);
+    LAUNCHED(1);
+}
+
+// =====================================================================================================
+// 2. quotient
+// =====================================================================================================
+__global__ void __launch_bounds__(128) k_quotient(QuotientArgs a) {
+    const int L = a.log_n + a.rate_bits;
+    const size_t N = size_t(1) << L;
+    size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    const u32 i = bitrev32((u32)pos, L);                       // natural point index
+    const u32 rmask = (1u << a.rate_bits) - 1;
+    // x = g * w_N^i
+    u64 x;
+    { size_t h = N >> 1; u64 wi = (i < h) ? __ldg(a.tw_fwd + h + i) : gl_neg(__ldg(a.tw_fwd + h + (i - h))); x = gl_mul(GL_GEN, wi); }
+    Wires cs = {a.cs_lde, N, pos}, w = {a.wires_lde, N, pos}, zs = {a.zs_lde, N, pos};
+    const size_t pos_next = bitrev32((u32)((i + (1u << a.rate_bits)) & (N - 1)), L);
+    Wires zs_next = {a.zs_lde, N, pos_next};
+    const u32 nch = a.num_challenges, npp = a.npp;
+    const u32 gate_off = nch + nch * (npp + 1);                // index of the first gate constraint among the vanishing terms
+
+    acc192 tot[MAX_CHALLENGES];
+#pragma unroll
+    for (int k = 0; k < MAX_CHALLENGES; k++) { tot[k].lo = 0; tot[k].hi = 0; tot[k].top = 0; }
+
+    // ---- L_0(x) (Z(x) - 1) and the partial-product checks ----
+    {
+        u64 l0 = gl_mul(a.zh_ev[i & rmask], gl_mul(a.n_inv, gl_inv(gl_sub(x, 1))));
+        for (u32 c = 0; c < nch; c++) {
+            u64 z = zs[c];
+            u64 t = gl_mul(l0, gl_sub(z, 1));
+            for (u32 k = 0; k < nch; k++) acc192_mad(tot[k], t, __ldg(a.apow + k * a.apow_stride + c));
+            u64 prev = z;
+            for (u32 kk = 0; kk <= npp; kk++) {
+                u64 num = 1, den = 1;
+                for (u32 j = kk * a.qdf; j < (kk + 1) * a.qdf && j < a.num_routed; j++) {
+                    u64 t0 = gl_add(w[j], a.gammas[c]);
+                    num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j), x))));
+                    den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], cs[a.num_constants + j])));
+                }
+                u64 next = kk < npp ? zs[nch + c * npp + kk] : zs_next[c];
+                u64 term = gl_sub(gl_mul(prev, num), gl_mul(next, den));
+                u32 tidx = nch + c * (npp + 1) + kk;
+                for (u32 k = 0; k < nch; k++) acc192_mad(tot[k], term, __ldg(a.apow + k * a.apow_stride + tidx));
+                prev = next;
+            }
+        }
+    }
+    // ---- gates ----
+    ConstraintSink sink; sink.apow = a.apow; sink.apow_stride = a.apow_stride;
+    Wires gc = {a.cs_lde + (size_t)a.num_selectors * N, N, pos};
+    u64 gsum[MAX_CHALLENGES] = {0, 0};
+    for (u32 gi = 0; gi < a.num_gates; gi++) {
+        const GateDesc g = a.gates[gi];
+        if (g.num_constraints == 0) continue;
+        u64 sel = cs[g.selector_index], filt = 1;
+        for (u32 r = g.group_start; r < g.group_end; r++) if (r != g.row) filt = gl_mul(filt, gl_sub((u64)r, sel));
+        if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
+        sink.reset();
+        eval_gate(g, gc, w, a.pi_hash, a.extra, sink);
+        for (u32 k = 0; k < nch; k++) gsum[k] = gl_add(gsum[k], gl_mul(filt, sink.result(k)));
+    }
+    for (u32 k = 0; k < nch; k++) {
+        // gate constraint i carries alpha^{gate_off + i}: multiply the gate sum by alpha^{gate_off}
+        acc192_mad(tot[k], gsum[k], __ldg(a.apow + k * a.apow_stride + gate_off));
+        u64 v = gl_mul(acc192_reduce(tot[k]), a.zh_inv[i & rmask]);
+        a.out[(size_t)k * N + i] = v;
+    }
+}
+void launch_quotient(const QuotientArgs &a, cudaStream_t st) {
+    size_t N = size_t(1) << (a.log_n + a.rate_bits);
+    k_quotient<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    LAUNCHED(1);
+}
+
+// big[ci] holds (br order) the coefficients of Q(g X): coefficient k of Q = big-coeff_k * g^{-k} (1/N already applied).
+// chunk m coefficient k' (k = m n + k') lives at position 8*br_n(k') + br_3(m).
+__global__ void k_quotient_split(const u64 *__restrict__ big, u64 *__restrict__ chunks, int log_n, int rate_bits, u32 nch) {
+    const size_t n = size_t(1) << log_n, N = n << rate_bits;
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)nch * N) return;
+    u32 ci = (u32)(idx / N); size_t rest = idx % N;
+    u32 m = (u32)(rest >> log_n), q = (u32)(rest & (n - 1));         // output: chunk m, br position q
+    u32 kp = bitrev32(q, log_n);
+    u64 k = (u64)m * n + kp;
+    u64 v = big[(size_t)ci * N + ((size_t)q << rate_bits) + bitrev32(m, rate_bits)];
+    u64 ginv = gl_inv(GL_GEN);
+    chunks[((size_t)ci * (1u << rate_bits) + m) * n + q] = gl_mul(v, gl_pow(ginv, k));
+}
+void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 nch, cudaStream_t st) {
+    size_t total = (size_t)nch << (log_n + rate_bits);
+    k_quotient_split<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_big, d_chunks, log_n, rate_bits, nch);
+    LAUNCHED(1);
+}
+
+// =====================================================================================================
+// 3. openings
+// =====================================================================================================
+struct Pows2 { gl2 v[32]; };
+__global__ void k_ext_pow_table(gl2 *table, int L, Pows2 p2) {
+    size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (q >= (size_t(1) << L)) return;
+    u32 e = bitrev32((u32)q, L);
+    gl2 r = gl2_make(1, 0);
+    for (int b = 0; b < L; b++) if (e & (1u << b)) r = gl2_mul(r, p2.v[b]);
+    table[q] = r;
+}
+void launch_ext_pow_table(gl2 *d_table, int L, const gl2 *h_pows2, cudaStream_t st) {
+    Pows2 p; for (int b = 0; b < 32; b++) p.v[b] = b < L ? h_pows2[b] : gl2_make(0, 0);
+    size_t n = size_t(1) << L;
+    k_ext_pow_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_table, L, p);
+    LAUNCHED(1);
+}
+__global__ void __launch_bounds__(256) k_eval_polys(const u64 *__restrict__ coeffs, int L, const gl2 *__restrict__ table, gl2 *__restrict__ out) {
+    __shared__ u64 sa[256], sb[256];
+    const size_t n = size_t(1) << L;
+    const u64 *c = coeffs + (size_t)blockIdx.x * n;
+    acc192 A = {0, 0, 0}, B = {0, 0, 0};
+    for (size_t q = threadIdx.x; q < n; q += 256) {
+        u64 v = c[q]; gl2 t = table[q];
+        acc192_mad(A, v, t.a); acc192_mad(B, v, t.b);
+    }
+    sa[threadIdx.x] = acc192_reduce(A); sb[threadIdx.x] = acc192_reduce(B);
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) { sa[threadIdx.x] = gl_add(sa[threadIdx.x], sa[threadIdx.x + off]); sb[threadIdx.x] = gl_add(sb[threadIdx.x], sb[threadIdx.x + off]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = gl2_make(sa[0], sb[0]);
+}
+void launch_eval_polys(const u64 *d_coeffs_br, size_t num_polys, int L, const gl2 *d_table, gl2 *d_out, cudaStream_t st) {
+    k_eval_polys<<<(unsigned)num_polys, 256, 0, st>>>(d_coeffs_br, L, d_table, d_out);
+    LAUNCHED(1);
+}
+
+// =====================================================================================================
+// 4. FRI: batching of all oracles into one extension-field codeword, folding, proof of work
+// =====================================================================================================
+__global__ void __launch_bounds__(128) k_fri_combine(FriCombineArgs a) {
+    const size_t N = size_t(1) << a.log_N;
+    size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    const u32 i = bitrev32((u32)pos, a.log_N);
+    u64 x;
+    { size_t h = N >> 1; u64 wi = (i < h) ? __ldg(a.tw_fwd + h + i) : gl_neg(__ldg(a.tw_fwd + h + (i - h))); x = gl_mul(GL_GEN, wi); }
+    acc192 A = {0, 0, 0}, B = {0, 0, 0};
+    u32 p = 0;
+    for (int o = 0; o < 4; o++) {
+        const u64 *base = a.lde[o] + pos;
+        for (u32 c = 0; c < a.cols[o]; c++, p++) {
+            u64 v = __ldg(base + (size_t)c * N);
+            gl2 ap = a.apow[p];
+            acc192_mad(A, v, ap.a); acc192_mad(B, v, ap.b);
+        }
+    }
+    gl2 F0 = gl2_make(acc192_reduce(A), acc192_reduce(B));
+    acc192 A1 = {0, 0, 0}, B1 = {0, 0, 0};
+    for (u32 c = 0; c < a.nch; c++) {
+        u64 v = __ldg(a.lde[2] + (size_t)c * N + pos);
+        gl2 ap = a.apow[c];
+        acc192_mad(A1, v, ap.a); acc192_mad(B1, v, ap.b);
+    }
+    gl2 F1 = gl2_make(acc192_reduce(A1), acc192_reduce(B1));
+    gl2 xe = gl2_make(x, 0);
+    gl2 t0 = gl2_mul(gl2_sub(F0, a.y0), gl2_inv(gl2_sub(xe, a.zeta)));
+    gl2 t1 = gl2_mul(gl2_sub(F1, a.y1), gl2_inv(gl2_sub(xe, a.gzeta)));
+    a.out[pos] = gl2_add(gl2_mul(t0, a.alpha_nch), t1);
+}
+void launch_fri_combine(const FriCombineArgs &a, cudaStream_t st) {
+    size_t N = size_t(1) << a.log_N;
+    k_fri_combine<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    LAUNCHED(1);
+}
+
+// one thread per coset of 2^ab values (consecutive in bit-reversed order)
+template <int AB>
+__global__ void __launch_bounds__(128) k_fri_fold(const gl2 *__restrict__ in, gl2 *__restrict__ out, int log_len, gl2 beta, u64 shift,
+                                                  const u64 *__restrict__ tw) {
+    constexpr int A = 1 << AB;
+    const size_t len = size_t(1) << log_len, nout = len >> AB;
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= nout) return;
+    // values in natural coset order: y[m] = in[A*i + br_AB(m)], at points x0 * w_A^m, x0 = shift * w_len^{br(i)}
+    gl2 y[A];
+#pragma unroll
+    for (int k = 0; k < A; k++) y[bitrev32(k, AB)] = in[A * i + k];
+    // inverse DFT of size A (DIF with inverse twiddles, output bit-reversed), unnormalised
+    u64 winv[A / 2];
+    { u64 wa = gl_inv(gl_root_of_unity(AB)); winv[0] = 1; for (int k = 1; k < A / 2; k++) winv[k] = gl_mul(winv[k - 1], wa); }
+#pragma unroll
+    for (int s = AB - 1; s >= 0; s--) {
+        const int h = 1 << s;
+#pragma unroll
+        for (int e = 0; e < A; e++) {
+            if (e & h) continue;
+            int j = e & (h - 1);
+            gl2 u = y[e], v = y[e + h];
+            y[e] = gl2_add(u, v);
+            y[e + h] = gl2_scale(gl2_sub(u, v), winv[j * (A / 2 / h)]);
+        }
+    }
+    // d_t = y[br(t)] / A ; folded = sum_t (beta / x0)^t d_t
+    u32 e = bitrev32((u32)i, log_len - AB);
+    u64 wl;
+    { size_t hh = len >> 1; wl = (len == 1) ? 1 : ((e < hh) ? __ldg(tw + hh + e) : gl_neg(__ldg(tw + hh + (e - hh)))); }
+    u64 x0 = gl_mul(shift, wl);
+    gl2 r = gl2_scale(beta, gl_inv(x0));
+    gl2 acc = gl2_make(0, 0);
+#pragma unroll
+    for (int t = A - 1; t >= 0; t--) acc = gl2_add(gl2_mul(acc, r), y[bitrev32(t, AB)]);
+    out[i] = gl2_scale(acc, gl_inv((u64)A));
+}
+void launch_fri_fold(const gl2 *d_in, gl2 *d_out, int log_len, int arity_bits, gl2 beta, u64 shift, const u64 *tw_fwd, cudaStream_t st) {
+    size_t nout = size_t(1) << (log_len - arity_bits);
+    unsigned blocks = (unsigned)((nout + 127) / 128);
+    switch (arity_bits) {
+    case 1: k_fri_fold<1><<<blocks, 128, 0, st>>>(d_in, d_out, log_len, beta, shift, tw_fwd); break;
+    case 2: k_fri_fold<2><<<blocks, 128, 0, st>>>(d_in, d_out, log_len, beta, shift, tw_fwd); break;
+    case 3: k_fri_fold<3><<<blocks, 128, 0, st>>>(d_in, d_out, log_len, beta, shift, tw_fwd); break;
+    case 4: k_fri_fold<4><<<blocks, 128, 0, st>>>(d_in, d_out, log_len, beta, shift, tw_fwd); break;
+    default: throw CudaErr{cudaErrorInvalidValue, __FILE__, __LINE__};
+    }
+    LAUNCHED(1);
+}
+
+struct PowState { u64 s[12]; };
+__global__ void __launch_bounds__(128) k_pow(PowState base, int pos, u64 start, u64 count, int bits, unsigned long long *result) {
+    u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    u64 cand = start + t;
+    if (cand >= GL_P) return;
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = base.s[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (i == pos) s[i] = cand;
+    poseidon_permute(s);
+    if ((s[7] >> (64 - bits)) == 0) atomicMin(result, (unsigned long long)cand);
+}
+void launch_pow(const u64 state[12], int pos, u64 start, u64 count, int bits, u64 *d_result, cudaStream_t st) {
+    PowState b; for (int i = 0; i < 12; i++) b.s[i] = state[i];
+    k_pow<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(b, pos, start, count, bits, (unsigned long long *)d_result);
+    LAUNCHED(1);
+}
+
+// dst[c] = src[c * stride + index]
+__global__ void k_gather(const u64 *__restrict__ src, size_t stride, size_t count, size_t index, u64 *__restrict__ dst) {
+    size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (c < count) dst[c] = src[c * stride + index];
+}
+void launch_gather(const u64 *d_src, size_t src_stride, size_t count, size_t index, u64 *d_dst, cudaStream_t st) {
+    k_gather<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_src, src_stride, count, index, d_dst);
+    LAUNCHED(1);
+}

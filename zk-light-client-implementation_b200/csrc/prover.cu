@@ -1,14 +1,551 @@
-// b200_circuit_upload / b200_prove: placeholder until the full prover lands (returns B200_ERR_UNSUPPORTED).
+// b200_circuit_upload / b200_prove: the GPU plonky2 prover (PoseidonGoldilocksConfig, D = 2, zero_knowledge = false,
+// no lookups).  Replaces upstream plonky2::plonk::prover::prove after witness generation
+// (call sites: near_bft_finality/src/prove_crypto/ed25519.rs:60,100, recursion.rs:95, sha256.rs:82,
+//  prove_block_data/keys_stakes.rs:244, primitives.rs:108,158,343) and the constants/sigmas commitment of
+// CircuitBuilder::build (ed25519.rs:33, recursion.rs:94, sha256.rs:78).
+//
+// Pipeline (all device-resident, column-major, LDE rows bit-reversed; host only runs the Fiat-Shamir sponge):
+//   wires --iNTT--> coeffs --coset LDE--> [W][8n] --Poseidon leaves/Merkle--> cap  ==> beta, gamma
+//   partial products + Z (scan) --commit--> cap                                   ==> alpha
+//   quotient on the 8n coset (gate table) --iNTT--> 8 chunks/challenge --commit--> cap ==> zeta
+//   openings (dot products with zeta powers)                                      ==> fri alpha
+//   FRI: value-space batching of all four oracles, arity-16 folds + Merkle per layer ==> betas
+//   final poly (host, tiny), 16-bit PoW grind (min nonce), 28 query openings (gather kernel)
 #include "../../include/b200_plonky2.h"
 #include "ctx.h"
-extern "C" {
-int b200_circuit_upload(b200_ctx *ctx, const b200_common *, const uint64_t *, const uint64_t[4], uint64_t *, b200_circuit **) {
-    if (ctx) ctx->err = "b200_circuit_upload: not implemented yet"; return B200_ERR_UNSUPPORTED; }
-void b200_circuit_free(b200_circuit *) {}
-int b200_prove(b200_ctx *ctx, const b200_circuit *, const uint64_t *, const uint64_t *, size_t, uint64_t, uint8_t **, size_t *) {
-    if (ctx) ctx->err = "b200_prove: not implemented yet"; return B200_ERR_UNSUPPORTED; }
-int b200_prove_dev(b200_ctx *ctx, const b200_circuit *, const uint64_t *, const uint64_t *, size_t, uint64_t, uint8_t **, size_t *) {
-    if (ctx) ctx->err = "b200_prove_dev: not implemented yet"; return B200_ERR_UNSUPPORTED; }
-int b200_fri_fold(b200_ctx *ctx, const uint64_t *, uint32_t, uint32_t, const uint64_t[2], uint64_t, uint64_t *) {
-    if (ctx) ctx->err = "b200_fri_fold: not implemented yet"; return B200_ERR_UNSUPPORTED; }
+#include "plonk.cuh"
+#include "poseidon.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------------
+// gate id parsing (plonky2 Gate::id() strings as they appear in common_data.json)
+// ------------------------------------------------------------------------------------------------
+static bool starts_with(const char *s, const char *p) { return strncmp(s, p, strlen(p)) == 0; }
+
+static bool parse_gate(const char *id, GateDesc &g, std::vector<u64> &extra) {
+    memset(&g, 0, sizeof g);
+    unsigned a = 0, b = 0, c = 0;
+    if (strcmp(id, "NoopGate") == 0) { g.kind = G_NOOP; g.num_constraints = 0; return true; }
+    if (sscanf(id, "ConstantGate { num_consts: %u }", &a) == 1) { g.kind = G_CONSTANT; g.p[0] = a; g.num_constraints = a; return true; }
+    if (strcmp(id, "PublicInputGate") == 0) { g.kind = G_PUBLIC_INPUT; g.num_constraints = 4; return true; }
+    if (sscanf(id, "ArithmeticGate { num_ops: %u }", &a) == 1) { g.kind = G_ARITHMETIC; g.p[0] = a; g.num_constraints = a; return true; }
+    if (sscanf(id, "ArithmeticExtensionGate { num_ops: %u }", &a) == 1) { g.kind = G_ARITHMETIC_EXT; g.p[0] = a; g.num_constraints = 2 * a; return true; }
+    if (sscanf(id, "MulExtensionGate { num_ops: %u }", &a) == 1) { g.kind = G_MUL_EXT; g.p[0] = a; g.num_constraints = 2 * a; return true; }
+    if (sscanf(id, "BaseSumGate { num_limbs: %u } + Base: %u", &a, &b) == 2) { g.kind = G_BASE_SUM; g.p[0] = a; g.p[1] = b; g.num_constraints = 1 + a; return true; }
+    if (sscanf(id, "ReducingGate { num_coeffs: %u }", &a) == 1) { g.kind = G_REDUCING; g.p[0] = a; g.num_constraints = 2 * a; return true; }
+    if (sscanf(id, "ReducingExtensionGate { num_coeffs: %u }", &a) == 1) { g.kind = G_REDUCING_EXT; g.p[0] = a; g.num_constraints = 2 * a; return true; }
+    if (sscanf(id, "RandomAccessGate { bits: %u, num_copies: %u, num_extra_constants: %u", &a, &b, &c) == 3) {
+        if (a > 6) return false;
+        g.kind = G_RANDOM_ACCESS; g.p[0] = a; g.p[1] = b; g.p[2] = c; g.num_constraints = b * (a + 2) + c; return true; }
+    if (starts_with(id, "PoseidonMdsGate")) { g.kind = G_POSEIDON_MDS; g.num_constraints = 24; return true; }
+    if (starts_with(id, "PoseidonGate")) { g.kind = G_POSEIDON; g.num_constraints = 123; return true; }
+    if (sscanf(id, "CosetInterpolationGate { subgroup_bits: %u, degree: %u, barycentric_weights: [", &a, &b) == 2) {
+        const char *p = strchr(id, '['); if (!p) return false; p++;
+        g.kind = G_COSET_INTERPOLATION; g.p[0] = a; g.p[1] = b; g.extra_off = (u32)extra.size();
+        unsigned np = 1u << a;
+        for (unsigned i = 0; i < np; i++) {
+            char *end; unsigned long long v = strtoull(p, &end, 10); if (end == p) return false;
+            extra.push_back((u64)v); p = end; while (*p == ',' || *p == ' ') p++;
+        }
+        if (b < 2 || a > 6) return false;
+        unsigned n_inter = (np - 2) / (b - 1);
+        g.num_constraints = 2 + 4 * n_inter + 2; return true; }
+    if (sscanf(id, "U32ArithmeticGate { num_ops: %u", &a) == 1) { g.kind = G_U32_ARITHMETIC; g.p[0] = a; g.num_constraints = 36 * a; return true; }
+    if (sscanf(id, "U32AddManyGate { num_addends: %u, num_ops: %u", &a, &b) == 2) { g.kind = G_U32_ADD_MANY; g.p[0] = a; g.p[1] = b; g.num_constraints = 21 * b; return true; }
+    if (sscanf(id, "U32SubtractionGate { num_ops: %u", &a) == 1) { g.kind = G_U32_SUBTRACTION; g.p[0] = a; g.num_constraints = 19 * a; return true; }
+    if (sscanf(id, "U32RangeCheckGate { num_input_limbs: %u", &a) == 1) { g.kind = G_U32_RANGE_CHECK; g.p[0] = a; g.num_constraints = 17 * a; return true; }
+    if (sscanf(id, "U32InterleaveGate { num_ops: %u", &a) == 1) { g.kind = G_U32_INTERLEAVE; g.p[0] = a; g.num_constraints = 34 * a; return true; }
+    if (sscanf(id, "UninterleaveToU32Gate { num_ops: %u", &a) == 1) { g.kind = G_UNINTERLEAVE_U32; g.p[0] = a; g.num_constraints = 67 * a; return true; }
+    if (sscanf(id, "UninterleaveToB32Gate { num_ops: %u", &a) == 1) { g.kind = G_UNINTERLEAVE_B32; g.p[0] = a; g.num_constraints = 67 * a; return true; }
+    if (sscanf(id, "ComparisonGate { num_bits: %u, num_chunks: %u", &a, &b) == 2) {
+        if (b == 0) return false;
+        unsigned cb = (a + b - 1) / b; if (cb > 6) return false;
+        g.kind = G_COMPARISON; g.p[0] = a; g.p[1] = b; g.num_constraints = 6 + 5 * b + cb; return true; }
+    return false;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Fiat-Shamir challenger (host).  Semantics: gnark-plonky2-verifier/challenger/challenger.go:42-165.
+// ------------------------------------------------------------------------------------------------
+struct Challenger {
+    u64 st[12]; u64 in[8]; int nin; u64 out[8]; int nout;
+    Challenger() { memset(this, 0, sizeof *this); }
+    void duplex() {
+        for (int i = 0; i < nin; i++) st[i] = in[i];
+        nin = 0; poseidon_permute(st);
+        for (int i = 0; i < 8; i++) out[i] = st[i];
+        nout = 8;
+    }
+    void observe(u64 x) { nout = 0; in[nin++] = x; if (nin == 8) duplex(); }
+    void observe_n(const u64 *x, size_t n) { for (size_t i = 0; i < n; i++) observe(x[i]); }
+    void observe_ext(gl2 e) { observe(e.a); observe(e.b); }
+    u64 get() { if (nin || !nout) duplex(); return out[--nout]; }
+    gl2 get_ext() { gl2 r; r.a = get(); r.b = get(); return r; }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct b200_circuit {
+    b200_ctx *ctx;
+    u32 num_wires, num_routed, num_constants, num_challenges, degree_bits, rate_bits, cap_height, pow_bits, num_queries,
+        qdf, npp, num_gate_constraints, num_pi, num_selectors;
+    std::vector<u32> arity_bits;
+    std::vector<GateDesc> gates;
+    std::vector<u64> k_is;
+    DevBuf d_gates, d_extra, d_kis;
+    DevBuf cs_coeffs, cs_lde, cs_digests, sigma_values;
+    u64 digest[4];
+};
+
+struct Arena {      // bump allocator over one device allocation, reset per prove
+    u8 *base = nullptr; size_t cap = 0, off = 0;
+    u64 *take(size_t n_u64) { size_t b = (n_u64 * 8 + 255) & ~size_t(255); if (off + b > cap) throw ApiErr{B200_ERR_OOM, "arena exhausted"}; u64 *p = (u64 *)(base + off); off += b; return p; }
+};
+static u8 *ctx_arena(b200_ctx *ctx, size_t bytes);   // defined below (grow-only scratch owned by the context)
+
+static void put_u64(std::vector<uint8_t> &o, u64 x) { for (int i = 0; i < 8; i++) o.push_back((uint8_t)(x >> (8 * i))); }
+static void put_words(std::vector<uint8_t> &o, const u64 *w, size_t n) { for (size_t i = 0; i < n; i++) put_u64(o, w[i]); }
+
+// host-side tiny NTT (final polynomial only)
+static void host_ntt(std::vector<u64> &a, int logn, bool inverse) {
+    size_t n = size_t(1) << logn;
+    for (size_t i = 0; i < n; i++) { size_t j = bitrev32((u32)i, logn); if (i < j) std::swap(a[i], a[j]); }
+    u64 wn = gl_root_of_unity(logn); if (inverse) wn = gl_inv(wn);
+    for (int s = 1; s <= logn; s++) {
+        size_t m = size_t(1) << s, h = m >> 1; u64 wm = gl_pow(wn, n >> s);
+        for (size_t k = 0; k < n; k += m) { u64 w = 1; for (size_t j = 0; j < h; j++) { u64 t = gl_mul(w, a[k + j + h]), u = a[k + j]; a[k + j] = gl_add(u, t); a[k + j + h] = gl_sub(u, t); w = gl_mul(w, wm); } }
+    }
+    if (inverse) { u64 ni = gl_inv((u64)n % GL_P); for (auto &x : a) x = gl_mul(x, ni); }
+}
+
+struct CopyDesc { const u64 *src; u64 stride; u32 count; u32 dst_off; };
+__global__ void k_copy_descs(const CopyDesc *__restrict__ d, u64 *__restrict__ dst) {
+    CopyDesc c = d[blockIdx.x];
+    for (u32 i = threadIdx.x; i < c.count; i += blockDim.x) dst[c.dst_off + i] = c.src[(size_t)i * c.stride];
+}
+
+static void dump_dev(const char *dir, const char *name, const void *d, size_t bytes, cudaStream_t st) {
+    if (!dir) return;
+    std::vector<uint8_t> h(bytes);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), d, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::string p = std::string(dir) + "/" + name;
+    FILE *f = fopen(p.c_str(), "wb"); if (f) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+}
+
+static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in, bool wires_on_device, const u64 *pis, size_t n_pis,
+                      u64 pow_hint, uint8_t **proof_out, size_t *proof_len) {
+    cudaStream_t st = ctx->stream;
+    const int nlog = (int)k->degree_bits, rb = (int)k->rate_bits, chh = (int)k->cap_height;
+    const int Llog = nlog + rb;
+    const size_t n = size_t(1) << nlog, N = n << rb;
+    const u32 W = k->num_wires, R = k->num_routed, NC = k->num_constants, nch = k->num_challenges, qdf = k->qdf, npp = k->npp;
+    const u32 nzp = nch * (1 + npp), nq = nch * qdf;
+    const size_t capw = size_t(4) << chh;
+    const char *dbg = getenv("B200_DEBUG_DUMP");
+    if (n_pis != k->num_pi) throw ApiErr{B200_ERR_BAD_ARG, "b200_prove: wrong number of public inputs"};
+    ntt_tables_ensure(ctx->tw, Llog, st);
+
+    // ---- arena layout ----
+    const size_t dig_u64 = merkle_num_u64(Llog, chh);
+    size_t need = 0;
+    auto rnd = [](size_t u) { return (u * 8 + 255) & ~size_t(255); };
+    need += (wires_on_device ? 0 : rnd((size_t)W * n)) + rnd((size_t)W * n) + rnd((size_t)W * N) + rnd(dig_u64);      // wires
+    need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd((size_t)nch * (npp + 2) * n + 8192) + rnd(8);   // zs
+    need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64);                        // quotient
+    need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)); // openings tables
+    need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
+    Arena A; A.base = ctx_arena(ctx, need + (1 << 20)); A.cap = need + (1 << 20);
+
+    // ---- public input hash, wires commitment ----
+    u64 pi_hash[4]; poseidon_hash_no_pad_host(pis, n_pis, pi_hash);
+    const u64 *d_wires;
+    if (wires_on_device) d_wires = wires_in;
+    else { PhaseTimer tm(ctx, "h2d_wires"); u64 *t = A.take((size_t)W * n); CUDA_TRY(cudaMemcpyAsync(t, wires_in, (size_t)W * n * 8, cudaMemcpyHostToDevice, st)); d_wires = t; }
+    u64 *w_coeffs = A.take((size_t)W * n), *w_lde = A.take((size_t)W * N), *w_dig = A.take(dig_u64);
+    commit_values(ctx, d_wires, W, nlog, rb, chh, w_coeffs, w_lde, w_dig);
+    std::vector<u64> cap_w(capw), cap_z(capw), cap_q(capw);
+    CUDA_TRY(cudaMemcpyAsync(cap_w.data(), w_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+
+    Challenger ch;
+    ch.observe_n(k->digest, 4); ch.observe_n(pi_hash, 4); ch.observe_n(cap_w.data(), capw);
+    u64 betas[MAX_CHALLENGES] = {0, 0}, gammas[MAX_CHALLENGES] = {0, 0}, alphas[MAX_CHALLENGES] = {0, 0};
+    for (u32 i = 0; i < nch; i++) betas[i] = ch.get();
+    for (u32 i = 0; i < nch; i++) gammas[i] = ch.get();
+
+    // ---- partial products + Z ----
+    u64 *zs_vals = A.take((size_t)nzp * n), *zs_coeffs = A.take((size_t)nzp * n), *zs_lde = A.take((size_t)nzp * N), *zs_dig = A.take(dig_u64);
+    u64 *pp_scratch = A.take((size_t)nch * (npp + 2) * n + 8192), *d_final_prod = A.take(8);
+    { PhaseTimer t(ctx, "partial_products");
+    launch_partial_products(d_wires, k->sigma_values.u(), k->d_kis.u(), nlog, R, npp, qdf, nch, betas, gammas, ctx->tw.fwd, zs_vals, pp_scratch, d_final_prod, st); }
+    commit_values(ctx, zs_vals, nzp, nlog, rb, chh, zs_coeffs, zs_lde, zs_dig);
+    u64 final_prod[MAX_CHALLENGES];
+    CUDA_TRY(cudaMemcpyAsync(cap_z.data(), zs_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(final_prod, d_final_prod, nch * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (u32 i = 0; i < nch; i++) if (final_prod[i] != 1) throw ApiErr{B200_ERR_UNSATISFIED, "permutation argument: grand product != 1 (copy constraints violated)"};
+    if (dbg) dump_dev(dbg, "zs_pp_values.bin", zs_vals, (size_t)nzp * n * 8, st);
+    ch.observe_n(cap_z.data(), capw);
+    for (u32 i = 0; i < nch; i++) alphas[i] = ch.get();
+
+    // ---- quotient ----
+    const u32 gate_off = nch + nch * (npp + 1);
+    const u32 apow_stride = gate_off + k->num_gate_constraints + 1;
+    {
+        std::vector<u64> apow((size_t)MAX_CHALLENGES * apow_stride, 0);
+        for (u32 c = 0; c < nch; c++) { u64 p = 1; for (u32 i = 0; i < apow_stride; i++) { apow[(size_t)c * apow_stride + i] = p; p = gl_mul(p, alphas[c]); } }
+        u64 *d_apow = A.take(apow.size());
+        CUDA_TRY(cudaMemcpyAsync(d_apow, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, st));
+        u64 *q_vals = A.take((size_t)nch * N), *q_big = A.take((size_t)nch * N);
+        QuotientArgs qa; memset(&qa, 0, sizeof qa);
+        qa.cs_lde = k->cs_lde.u(); qa.wires_lde = w_lde; qa.zs_lde = zs_lde; qa.out = q_vals;
+        qa.gates = (const GateDesc *)k->d_gates.p; qa.extra = k->d_extra.u(); qa.k_is = k->d_kis.u(); qa.apow = d_apow; qa.tw_fwd = ctx->tw.fwd;
+        qa.apow_stride = apow_stride; qa.num_gates = (u32)k->gates.size(); qa.num_selectors = k->num_selectors; qa.num_constants = NC;
+        qa.num_routed = R; qa.num_wires = W; qa.num_challenges = nch; qa.npp = npp; qa.qdf = qdf; qa.num_gate_constraints = k->num_gate_constraints;
+        qa.log_n = nlog; qa.rate_bits = rb;
+        for (u32 c = 0; c < nch; c++) { qa.betas[c] = betas[c]; qa.gammas[c] = gammas[c]; }
+        for (int i = 0; i < 4; i++) qa.pi_hash[i] = pi_hash[i];
+        {
+            u64 g_pow_n = gl_pow(GL_GEN, (u64)n), wr = gl_root_of_unity(rb), x = 1;
+            for (u32 i = 0; i < (1u << rb); i++) { qa.zh_ev[i] = gl_sub(gl_mul(g_pow_n, x), 1); qa.zh_inv[i] = gl_inv(qa.zh_ev[i]); x = gl_mul(x, wr); }
+            qa.n_inv = gl_inv((u64)n % GL_P);
+        }
+        { PhaseTimer t(ctx, "quotient"); launch_quotient(qa, st); }
+        // coefficients of Q(gX): DIF inverse NTT natural -> bit-reversed, scaled by 1/N
+        { PhaseTimer t(ctx, "quotient_intt"); ntt_dif(ctx->tw, q_vals, N, false, q_big, N, Llog, nch, 0, nullptr, true, gl_inv((u64)N % GL_P), st); }
+        // q_vals is free again: reuse as chunk coefficient storage?  keep separate buffers for clarity
+        (void)q_vals;
+        ctx->tmp_q_big = q_big;
+    }
+    u64 *q_coeffs = A.take((size_t)nq * n), *q_lde = A.take((size_t)nq * N), *q_dig = A.take(dig_u64);
+    launch_quotient_split(ctx->tmp_q_big, q_coeffs, nlog, rb, nch, st);
+    commit_coeffs(ctx, q_coeffs, nq, nlog, rb, chh, q_lde, q_dig);
+    CUDA_TRY(cudaMemcpyAsync(cap_q.data(), q_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (dbg) dump_dev(dbg, "quotient_coeffs_br.bin", q_coeffs, (size_t)nq * n * 8, st);
+    ch.observe_n(cap_q.data(), capw);
+    gl2 zeta = ch.get_ext();
+    if (gl2_eq(gl2_pow(zeta, (u64)n), gl2_make(1, 0))) throw ApiErr{B200_ERR_UNSATISFIED, "opening point zeta lies in the subgroup"};
+
+    // ---- openings ----
+    const u64 w_n = gl_root_of_unity(nlog);
+    gl2 gzeta = gl2_scale(zeta, w_n);
+    const size_t total_polys = (size_t)NC + R + W + nzp + nq;
+    gl2 *d_tab = (gl2 *)A.take(2 * n), *d_tab2 = (gl2 *)A.take(2 * n);
+    gl2 *d_open = (gl2 *)A.take(2 * (total_polys + nch));
+    {
+        PhaseTimer tm(ctx, "openings");
+        gl2 p2[32]; gl2 t = zeta; for (int b = 0; b < nlog; b++) { p2[b] = t; t = gl2_mul(t, t); }
+        launch_ext_pow_table(d_tab, nlog, p2, st);
+        t = gzeta; for (int b = 0; b < nlog; b++) { p2[b] = t; t = gl2_mul(t, t); }
+        launch_ext_pow_table(d_tab2, nlog, p2, st);
+        size_t off = 0;
+        launch_eval_polys(k->cs_coeffs.u(), NC + R, nlog, d_tab, d_open + off, st); off += NC + R;
+        launch_eval_polys(w_coeffs, W, nlog, d_tab, d_open + off, st); off += W;
+        launch_eval_polys(zs_coeffs, nzp, nlog, d_tab, d_open + off, st); off += nzp;
+        launch_eval_polys(q_coeffs, nq, nlog, d_tab, d_open + off, st); off += nq;
+        launch_eval_polys(zs_coeffs, nch, nlog, d_tab2, d_open + off, st);
+    }
+    std::vector<gl2> open(total_polys + nch);
+    CUDA_TRY(cudaMemcpyAsync(open.data(), d_open, open.size() * sizeof(gl2), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < total_polys; i++) ch.observe_ext(open[i]);
+    for (u32 i = 0; i < nch; i++) ch.observe_ext(open[total_polys + i]);
+
+    // ---- FRI ----
+    gl2 fri_alpha = ch.get_ext();
+    std::vector<gl2> apow(total_polys);
+    { gl2 p = gl2_make(1, 0); for (size_t i = 0; i < total_polys; i++) { apow[i] = p; p = gl2_mul(p, fri_alpha); } }
+    gl2 y0 = gl2_make(0, 0), y1 = gl2_make(0, 0);
+    for (size_t i = 0; i < total_polys; i++) y0 = gl2_add(y0, gl2_mul(open[i], apow[i]));
+    for (u32 i = 0; i < nch; i++) y1 = gl2_add(y1, gl2_mul(open[total_polys + i], apow[i]));
+    gl2 *d_apow2 = (gl2 *)A.take(2 * total_polys);
+    CUDA_TRY(cudaMemcpyAsync(d_apow2, apow.data(), total_polys * sizeof(gl2), cudaMemcpyHostToDevice, st));
+    gl2 *fri_a = (gl2 *)A.take(2 * N), *fri_b = (gl2 *)A.take(2 * N);
+    {
+        FriCombineArgs fa; memset(&fa, 0, sizeof fa);
+        fa.lde[0] = k->cs_lde.u(); fa.lde[1] = w_lde; fa.lde[2] = zs_lde; fa.lde[3] = q_lde;
+        fa.cols[0] = NC + R; fa.cols[1] = W; fa.cols[2] = nzp; fa.cols[3] = nq;
+        fa.apow = d_apow2; fa.total_polys = (u32)total_polys; fa.nch = nch; fa.y0 = y0; fa.y1 = y1; fa.zeta = zeta; fa.gzeta = gzeta;
+        fa.alpha_nch = gl2_pow(fri_alpha, nch); fa.tw_fwd = ctx->tw.fwd; fa.log_N = Llog; fa.out = fri_a;
+        { PhaseTimer t(ctx, "fri_combine"); launch_fri_combine(fa, st); }
+    }
+    if (dbg) dump_dev(dbg, "fri_values0.bin", fri_a, N * 16, st);
+    // commit phase: layers[l] = values (device, kept for the query phase), digests
+    struct Layer { gl2 *vals; u64 *dig; int log_len, log_leaves; size_t dig_u64; };
+    std::vector<Layer> layers;
+    std::vector<std::vector<u64>> layer_caps;
+    std::vector<gl2> fri_betas;
+    gl2 *cur = fri_a; int cur_log = Llog; u64 shift = GL_GEN;
+    size_t fri_pool_used = 0; gl2 *pool = fri_b;
+    for (size_t li = 0; li < k->arity_bits.size(); li++) {
+        int ab = (int)k->arity_bits[li];
+        PhaseTimer tl(ctx, "fri_layers");
+        Layer Ly; Ly.vals = cur; Ly.log_len = cur_log; Ly.log_leaves = cur_log - ab; Ly.dig_u64 = merkle_num_u64(Ly.log_leaves, chh);
+        Ly.dig = A.take(Ly.dig_u64);
+        merkle_leaves_rowmajor((const u64 *)cur, size_t(2) << ab, Ly.log_leaves, Ly.dig, st);
+        merkle_build(Ly.dig, Ly.log_leaves, chh, st);
+        std::vector<u64> cap(capw);
+        CUDA_TRY(cudaMemcpyAsync(cap.data(), Ly.dig + Ly.dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ch.observe_n(cap.data(), capw);
+        gl2 beta = ch.get_ext();
+        fri_betas.push_back(beta); layer_caps.push_back(cap); layers.push_back(Ly);
+        gl2 *nxt = pool + fri_pool_used; fri_pool_used += size_t(1) << (cur_log - ab);
+        launch_fri_fold(cur, nxt, cur_log, ab, beta, shift, ctx->tw.fwd, st);
+        shift = gl_pow(shift, u64(1) << ab);
+        cur = nxt; cur_log -= ab;
+    }
+    // final polynomial (host): values on shift * H_{2^cur_log} in bit-reversed order -> coefficients
+    size_t fin_n = size_t(1) << cur_log;
+    std::vector<gl2> fin_vals(fin_n);
+    CUDA_TRY(cudaMemcpyAsync(fin_vals.data(), cur, fin_n * sizeof(gl2), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<u64> fa(fin_n), fb(fin_n);
+    for (size_t i = 0; i < fin_n; i++) { size_t r = bitrev32((u32)i, cur_log); fa[i] = fin_vals[r].a; fb[i] = fin_vals[r].b; }
+    host_ntt(fa, cur_log, true); host_ntt(fb, cur_log, true);
+    { u64 sinv = gl_inv(shift), s = 1; for (size_t i = 0; i < fin_n; i++) { fa[i] = gl_mul(fa[i], s); fb[i] = gl_mul(fb[i], s); s = gl_mul(s, sinv); } }
+    size_t fin_len = fin_n >> rb;
+    for (size_t i = fin_len; i < fin_n; i++) if (fa[i] || fb[i]) throw ApiErr{B200_ERR_UNSATISFIED, "witness does not satisfy the circuit: FRI final polynomial is not low-degree"};
+    for (size_t i = 0; i < fin_len; i++) { ch.observe(fa[i]); ch.observe(fb[i]); }
+
+    // ---- proof of work: minimum nonce (== reference with RAYON_NUM_THREADS=1), or a verified hint ----
+    u64 pow_witness = ~u64(0);
+    {
+        u64 base_state[12]; memcpy(base_state, ch.st, sizeof base_state);
+        for (int i = 0; i < ch.nin; i++) base_state[i] = ch.in[i];
+        int pos = ch.nin;
+        auto response = [&](u64 cand) { u64 s[12]; memcpy(s, base_state, sizeof s); s[pos] = cand; poseidon_permute(s); return s[7]; };
+        if (pow_hint && pow_hint < GL_P && (response(pow_hint) >> (64 - k->pow_bits)) == 0) pow_witness = pow_hint;
+        PhaseTimer tp(ctx, "pow");
+        u64 *d_res = A.take(8);
+        u64 start = 0; const u64 chunk = u64(1) << 22;
+        while (pow_witness == ~u64(0)) {
+            u64 init = ~u64(0);
+            CUDA_TRY(cudaMemcpyAsync(d_res, &init, 8, cudaMemcpyHostToDevice, st));
+            launch_pow(base_state, pos, start, chunk, (int)k->pow_bits, d_res, st);
+            u64 res; CUDA_TRY(cudaMemcpyAsync(&res, d_res, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (res != ~u64(0)) pow_witness = res;
+            start += chunk;
+            if (start > (u64(1) << 40)) throw ApiErr{B200_ERR_CUDA, "proof of work not found"};
+        }
+        ch.observe(pow_witness);
+        u64 resp = ch.get();
+        if (resp >> (64 - k->pow_bits)) throw ApiErr{B200_ERR_CUDA, "proof-of-work self-check failed"};
+    }
+
+    // ---- query rounds: gather leaves + Merkle paths with one kernel ----
+    const u64 *lde4[4] = {k->cs_lde.u(), w_lde, zs_lde, q_lde};
+    const u64 *dig4[4] = {k->cs_digests.u(), w_dig, zs_dig, q_dig};
+    const u32 cols4[4] = {NC + R, W, nzp, nq};
+    std::vector<CopyDesc> descs;
+    std::vector<size_t> qidx(k->num_queries);
+    u32 dst = 0;
+    for (u32 q = 0; q < k->num_queries; q++) {
+        size_t x = (size_t)(ch.get() % (u64)N);
+        qidx[q] = x;
+        for (int o = 0; o < 4; o++) {
+            descs.push_back({lde4[o] + x, (u64)N, cols4[o], dst}); dst += cols4[o];
+            const u64 *lvl = dig4[o]; size_t idx = x;
+            for (int lv = Llog; lv > chh; lv--) { descs.push_back({lvl + 4 * (idx ^ 1), 1, 4, dst}); dst += 4; lvl += size_t(4) << lv; idx >>= 1; }
+        }
+        size_t xi = x;
+        for (size_t li = 0; li < layers.size(); li++) {
+            int ab = (int)k->arity_bits[li]; size_t leaf = xi >> ab;
+            descs.push_back({(const u64 *)layers[li].vals + leaf * (size_t(2) << ab), 1, (u32)(2u << ab), dst}); dst += 2u << ab;
+            const u64 *lvl = layers[li].dig; size_t idx = leaf;
+            for (int lv = layers[li].log_leaves; lv > chh; lv--) { descs.push_back({lvl + 4 * (idx ^ 1), 1, 4, dst}); dst += 4; lvl += size_t(4) << lv; idx >>= 1; }
+            xi = leaf;
+        }
+    }
+    std::vector<u64> qdata(dst);
+    if (!descs.empty()) {
+        PhaseTimer tq(ctx, "query_gather");
+        CopyDesc *d_descs = (CopyDesc *)A.take(descs.size() * sizeof(CopyDesc) / 8 + 8);
+        u64 *d_q = A.take(dst + 8);
+        CUDA_TRY(cudaMemcpyAsync(d_descs, descs.data(), descs.size() * sizeof(CopyDesc), cudaMemcpyHostToDevice, st));
+        k_copy_descs<<<(unsigned)descs.size(), 64, 0, st>>>(d_descs, d_q);
+        LAUNCHED(1);
+        CUDA_TRY(cudaMemcpyAsync(qdata.data(), d_q, (size_t)dst * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+
+    // ---- serialize (ProofWithPublicInputs::to_bytes layout) ----
+    std::vector<uint8_t> out;
+    out.reserve(200000);
+    put_words(out, cap_w.data(), capw); put_words(out, cap_z.data(), capw); put_words(out, cap_q.data(), capw);
+    {
+        size_t o_sig = NC, o_w = NC + R, o_z = o_w + W, o_pp = o_z + nch, o_q = o_z + nzp;
+        auto put_ext = [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) { put_u64(out, open[i].a); put_u64(out, open[i].b); } };
+        put_ext(0, o_sig); put_ext(o_sig, o_w); put_ext(o_w, o_z); put_ext(o_z, o_pp);
+        put_ext(total_polys, total_polys + nch);          // plonk_zs_next
+        put_ext(o_pp, o_q); put_ext(o_q, total_polys);
+    }
+    for (auto &c : layer_caps) put_words(out, c.data(), capw);
+    {
+        size_t p = 0;
+        for (u32 q = 0; q < k->num_queries; q++) {
+            for (int o = 0; o < 4; o++) {
+                put_words(out, qdata.data() + p, cols4[o]); p += cols4[o];
+                int ns = Llog - chh; out.push_back((uint8_t)ns);
+                put_words(out, qdata.data() + p, (size_t)4 * ns); p += (size_t)4 * ns;
+            }
+            for (size_t li = 0; li < layers.size(); li++) {
+                size_t w = size_t(2) << k->arity_bits[li];
+                put_words(out, qdata.data() + p, w); p += w;
+                int ns = layers[li].log_leaves - chh; out.push_back((uint8_t)ns);
+                put_words(out, qdata.data() + p, (size_t)4 * ns); p += (size_t)4 * ns;
+            }
+        }
+    }
+    for (size_t i = 0; i < fin_len; i++) { put_u64(out, fa[i]); put_u64(out, fb[i]); }
+    put_u64(out, pow_witness);
+    put_u64(out, (u64)n_pis);
+    put_words(out, pis, n_pis);
+
+    if (dbg) {
+        std::string p = std::string(dbg) + "/challenges.txt";
+        FILE *f = fopen(p.c_str(), "w");
+        if (f) {
+            fprintf(f, "betas %llu %llu\ngammas %llu %llu\nalphas %llu %llu\nzeta %llu %llu\nfri_alpha %llu %llu\n", (unsigned long long)betas[0], (unsigned long long)betas[1],
+                    (unsigned long long)gammas[0], (unsigned long long)gammas[1], (unsigned long long)alphas[0], (unsigned long long)alphas[1],
+                    (unsigned long long)zeta.a, (unsigned long long)zeta.b, (unsigned long long)fri_alpha.a, (unsigned long long)fri_alpha.b);
+            fclose(f);
+        }
+    }
+    uint8_t *buf = (uint8_t *)malloc(out.size());
+    if (!buf) throw ApiErr{B200_ERR_OOM, "host allocation failed"};
+    memcpy(buf, out.data(), out.size());
+    *proof_out = buf; *proof_len = out.size();
+    return B200_OK;
+}
+
+static u8 *ctx_arena(b200_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->arena_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr; ctx->arena_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->arena, bytes));
+        ctx->arena_bytes = bytes;
+    }
+    return (u8 *)ctx->arena;
+}
+
+int ctx_fail(b200_ctx *ctx, int code, const std::string &msg);
+#define API_BEGIN(ctx) if (!(ctx)) return B200_ERR_BAD_ARG; try { cudaSetDevice((ctx)->device);
+#define API_END(ctx) } catch (const CudaErr &e) { \
+        char buf[256]; snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.e, cudaGetErrorString(e.e), e.file, e.line); \
+        cudaGetLastError(); \
+        return ctx_fail(ctx, e.e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA, buf); \
+    } catch (const ApiErr &e) { return ctx_fail(ctx, e.code, e.msg); \
+    } catch (const std::bad_alloc &) { return ctx_fail(ctx, B200_ERR_OOM, "host allocation failed"); \
+    } catch (const std::exception &e) { return ctx_fail(ctx, B200_ERR_BAD_ARG, e.what()); }
+
+extern "C" {
+
+int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_values, const uint64_t digest[4], uint64_t *cap_out, b200_circuit **out) {
+    API_BEGIN(ctx)
+    if (!c || !cs_values || !digest || !out) throw ApiErr{B200_ERR_BAD_ARG, "b200_circuit_upload: null argument"};
+    *out = nullptr;
+    if (c->hasher != 0) throw ApiErr{B200_ERR_UNSUPPORTED, "only PoseidonGoldilocksConfig (hasher 0) is implemented; the PoseidonBN128 wrap is a 'next' row"};
+    if (c->num_challenges == 0 || c->num_challenges > MAX_CHALLENGES) throw ApiErr{B200_ERR_UNSUPPORTED, "num_challenges must be 1 or 2"};
+    if (c->quotient_degree_factor != (1u << c->rate_bits)) throw ApiErr{B200_ERR_UNSUPPORTED, "quotient_degree_factor must equal 2^rate_bits"};
+    if (c->degree_bits < 2 || c->degree_bits + c->rate_bits > 28) throw ApiErr{B200_ERR_BAD_ARG, "degree_bits out of range"};
+    if (c->num_routed_wires > c->num_wires || c->num_partial_products + 1 > 16 ||
+        (c->num_partial_products + 1) * c->quotient_degree_factor < c->num_routed_wires)
+        throw ApiErr{B200_ERR_BAD_ARG, "inconsistent routed wires / partial products"};
+    if (c->cap_height > c->degree_bits + c->rate_bits || c->proof_of_work_bits == 0 || c->proof_of_work_bits > 32)
+        throw ApiErr{B200_ERR_BAD_ARG, "bad FRI config"};
+    std::unique_ptr<b200_circuit> k(new b200_circuit());
+    k->ctx = ctx;
+    k->num_wires = c->num_wires; k->num_routed = c->num_routed_wires; k->num_constants = c->num_constants; k->num_challenges = c->num_challenges;
+    k->degree_bits = c->degree_bits; k->rate_bits = c->rate_bits; k->cap_height = c->cap_height; k->pow_bits = c->proof_of_work_bits;
+    k->num_queries = c->num_query_rounds; k->qdf = c->quotient_degree_factor; k->npp = c->num_partial_products;
+    k->num_gate_constraints = c->num_gate_constraints; k->num_pi = c->num_public_inputs; k->num_selectors = c->num_selector_groups;
+    int bits_left = (int)c->degree_bits + (int)c->rate_bits;
+    for (u32 i = 0; i < c->num_reduction_arity_bits; i++) {
+        u32 ab = c->reduction_arity_bits[i];
+        if (ab < 1 || ab > 4 || bits_left - (int)ab < (int)c->cap_height) throw ApiErr{B200_ERR_UNSUPPORTED, "reduction arity bits must be in 1..4 and leave >= cap_height bits"};
+        k->arity_bits.push_back(ab); bits_left -= (int)ab;
+    }
+    if (bits_left < (int)c->rate_bits) throw ApiErr{B200_ERR_BAD_ARG, "too many FRI reductions"};
+    std::vector<u64> extra;
+    for (u32 i = 0; i < c->num_gates; i++) {
+        GateDesc g;
+        if (!c->gate_ids[i] || !parse_gate(c->gate_ids[i], g, extra)) { std::string m = "unsupported gate id: "; m += c->gate_ids[i] ? c->gate_ids[i] : "(null)"; throw ApiErr{B200_ERR_UNSUPPORTED, m}; }
+        u32 si = c->selector_indices[i];
+        if (si >= c->num_selector_groups) throw ApiErr{B200_ERR_BAD_ARG, "selector index out of range"};
+        g.selector_index = si; g.group_start = c->group_starts[si]; g.group_end = c->group_ends[si]; g.row = i;
+        if (g.num_constraints > c->num_gate_constraints) throw ApiErr{B200_ERR_BAD_ARG, "num_gate_constraints too small"};
+        k->gates.push_back(g);
+    }
+    k->k_is.assign(c->k_is, c->k_is + c->num_routed_wires);
+    memcpy(k->digest, digest, 32);
+    cudaStream_t st = ctx->stream;
+    const size_t n = size_t(1) << c->degree_bits, N = n << c->rate_bits;
+    const size_t cols = (size_t)c->num_constants + c->num_routed_wires;
+    k->d_gates.alloc(std::max<size_t>(1, k->gates.size()) * sizeof(GateDesc));
+    k->d_extra.alloc(std::max<size_t>(1, extra.size()) * 8);
+    k->d_kis.alloc(k->k_is.size() * 8);
+    CUDA_TRY(cudaMemcpyAsync(k->d_gates.p, k->gates.data(), k->gates.size() * sizeof(GateDesc), cudaMemcpyHostToDevice, st));
+    if (!extra.empty()) CUDA_TRY(cudaMemcpyAsync(k->d_extra.p, extra.data(), extra.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(k->d_kis.p, k->k_is.data(), k->k_is.size() * 8, cudaMemcpyHostToDevice, st));
+    DevBuf vals(cols * n * 8);
+    CUDA_TRY(cudaMemcpyAsync(vals.p, cs_values, cols * n * 8, cudaMemcpyHostToDevice, st));
+    k->cs_coeffs.alloc(cols * n * 8); k->cs_lde.alloc(cols * N * 8);
+    size_t nd = merkle_num_u64((int)(c->degree_bits + c->rate_bits), (int)c->cap_height);
+    k->cs_digests.alloc(nd * 8);
+    commit_values(ctx, vals.u(), cols, (int)c->degree_bits, (int)c->rate_bits, (int)c->cap_height, k->cs_coeffs.u(), k->cs_lde.u(), k->cs_digests.u());
+    k->sigma_values.alloc((size_t)c->num_routed_wires * n * 8);
+    CUDA_TRY(cudaMemcpyAsync(k->sigma_values.p, vals.u() + (size_t)c->num_constants * n, (size_t)c->num_routed_wires * n * 8, cudaMemcpyDeviceToDevice, st));
+    if (cap_out) CUDA_TRY(cudaMemcpyAsync(cap_out, k->cs_digests.u() + nd - (size_t(4) << c->cap_height), size_t(32) << c->cap_height, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *out = k.release();
+    return B200_OK;
+    API_END(ctx)
+}
+
+void b200_circuit_free(b200_circuit *c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    delete c;
+}
+
+int b200_prove(b200_ctx *ctx, const b200_circuit *circuit, const uint64_t *wires, const uint64_t *public_inputs, size_t n_pis,
+               uint64_t pow_witness_hint, uint8_t **proof_bytes, size_t *proof_len) {
+    API_BEGIN(ctx)
+    if (!circuit || !wires || !proof_bytes || !proof_len || (n_pis && !public_inputs)) throw ApiErr{B200_ERR_BAD_ARG, "b200_prove: null argument"};
+    if (circuit->ctx != ctx) throw ApiErr{B200_ERR_BAD_ARG, "b200_prove: circuit belongs to another context"};
+    return prove_impl(ctx, circuit, wires, false, public_inputs, n_pis, pow_witness_hint, proof_bytes, proof_len);
+    API_END(ctx)
+}
+
+int b200_prove_dev(b200_ctx *ctx, const b200_circuit *circuit, const uint64_t *d_wires, const uint64_t *public_inputs, size_t n_pis,
+                   uint64_t pow_witness_hint, uint8_t **proof_bytes, size_t *proof_len) {
+    API_BEGIN(ctx)
+    if (!circuit || !d_wires || !proof_bytes || !proof_len || (n_pis && !public_inputs)) throw ApiErr{B200_ERR_BAD_ARG, "b200_prove_dev: null argument"};
+    if (circuit->ctx != ctx) throw ApiErr{B200_ERR_BAD_ARG, "b200_prove_dev: circuit belongs to another context"};
+    return prove_impl(ctx, circuit, d_wires, true, public_inputs, n_pis, pow_witness_hint, proof_bytes, proof_len);
+    API_END(ctx)
+}
+
+int b200_fri_fold(b200_ctx *ctx, const uint64_t *values, uint32_t log_len, uint32_t arity_bits, const uint64_t beta[2], uint64_t shift, uint64_t *out) {
+    API_BEGIN(ctx)
+    if (!values || !beta || !out || arity_bits < 1 || arity_bits > 4 || log_len < arity_bits || log_len > 28) throw ApiErr{B200_ERR_BAD_ARG, "b200_fri_fold: bad arguments"};
+    ntt_tables_ensure(ctx->tw, (int)log_len, ctx->stream);
+    size_t len = size_t(1) << log_len, nout = len >> arity_bits;
+    DevBuf a(len * 16), b(nout * 16);
+    CUDA_TRY(cudaMemcpyAsync(a.p, values, len * 16, cudaMemcpyHostToDevice, ctx->stream));
+    launch_fri_fold((const gl2 *)a.p, (gl2 *)b.p, (int)log_len, (int)arity_bits, gl2_make(beta[0], beta[1]), shift, ctx->tw.fwd, ctx->stream);
+    CUDA_TRY(cudaMemcpyAsync(out, b.p, nout * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+    API_END(ctx)
+}
+
+}  // extern "C"
