@@ -322,7 +322,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         if (pow_hint && pow_hint < GL_P && (response(pow_hint) >> (64 - k->pow_bits)) == 0) pow_witness = pow_hint;
         PhaseTimer tp(ctx, "pow");
         u64 *d_res = A.take(8);
-        u64 start = 0; const u64 chunk = u64(1) << 22;
+        u64 start = 0; const u64 chunk = u64(1) << 18;   // expected 2^16 trials for a 16-bit PoW
         while (pow_witness == ~u64(0)) {
             u64 init = ~u64(0);
             CUDA_TRY(cudaMemcpyAsync(d_res, &init, 8, cudaMemcpyHostToDevice, st));
