@@ -32,15 +32,18 @@ void commit_values(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, i
     commit_coeffs(ctx, d_coeffs_br, cols, log_n, rate_bits, cap_height, d_lde, d_digests);
 }
 
-__global__ void k_permute_batch(u64 *st, size_t count) {
+__global__ void __launch_bounds__(128) k_permute_batch(u64 *st, size_t count) {
+    __shared__ u64 sm[12 * 128];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    u64 s[12];
+    const bool active = i < count;
+    if (!active) i = count - 1;
 #pragma unroll
-    for (int k = 0; k < 12; k++) s[k] = st[12 * i + k];
-    poseidon_permute(s);
+    for (int k = 0; k < 12; k++) sm[k * 128 + threadIdx.x] = st[12 * i + k];
+    poseidon_permute_smem(&sm[threadIdx.x], 128);
+    if (active) {
 #pragma unroll
-    for (int k = 0; k < 12; k++) st[12 * i + k] = s[k];
+        for (int k = 0; k < 12; k++) st[12 * i + k] = sm[k * 128 + threadIdx.x];
+    }
 }
 void poseidon_permute_batch(u64 *d_states, size_t count, cudaStream_t st) {
     k_permute_batch<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_states, count);

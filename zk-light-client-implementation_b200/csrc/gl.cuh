@@ -41,7 +41,15 @@ GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 
 GL_HD void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
 #ifdef __CUDA_ARCH__
-    lo = a * b; hi = __umul64hi(a, b);
+    // 4 x IMAD.WIDE.U32 with the 64-bit addend folded in + one 64-bit add (the 32x32->64 multiplier is the
+    // scarce unit on sm_100a: 25 /clk/SM, see profiles/int_peak_r01.jsonl)
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    const u64 p00 = (u64)a0 * b0;
+    const u64 t = (u64)a0 * b1 + (p00 >> 32);          // cannot overflow: (2^32-1)^2 + 2^32-1 < 2^64
+    const u64 u = (u64)a1 * b0 + (u32)t;
+    const u64 h = (u64)a1 * b1 + (t >> 32);
+    hi = h + (u >> 32);
+    lo = (u << 32) | (u32)p00;
 #else
     unsigned __int128 p = (unsigned __int128)a * b; lo = (u64)p; hi = (u64)(p >> 64);
 #endif
@@ -50,6 +58,26 @@ GL_HD void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
 // (hi*2^64 + lo) mod p, result in [0, 2^64) (not necessarily canonical).
 // 2^64 == 2^32 - 1, 2^96 == -1 (mod p).
 GL_HD u64 gl_reduce128_nc(u64 lo, u64 hi) {
+#ifdef __CUDA_ARCH__
+    u32 rl, rh;
+    asm("{\n\t"
+        ".reg .u32 t0l, t0h, bm, t1l, t1h, cm;\n\t"
+        "sub.cc.u32 t0l, %2, %5;\n\t"        // t0 = lo - (hi >> 32)
+        "subc.cc.u32 t0h, %3, 0;\n\t"
+        "subc.u32 bm, 0, 0;\n\t"             // borrow mask: 0 or 0xFFFFFFFF (== EPS)
+        "sub.cc.u32 t0l, t0l, bm;\n\t"       // t0 -= EPS on borrow
+        "subc.u32 t0h, t0h, 0;\n\t"
+        "sub.cc.u32 t1l, 0, %4;\n\t"         // t1 = (hi_lo << 32) - hi_lo
+        "subc.u32 t1h, %4, 0;\n\t"
+        "add.cc.u32 %0, t0l, t1l;\n\t"
+        "addc.cc.u32 %1, t0h, t1h;\n\t"
+        "addc.u32 cm, 0, 0;\n\t"
+        "neg.s32 cm, cm;\n\t"                // carry mask
+        "add.cc.u32 %0, %0, cm;\n\t"         // += EPS on carry
+        "addc.u32 %1, %1, 0;\n\t"
+        "}" : "=&r"(rl), "=&r"(rh) : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+    return ((u64)rh << 32) | rl;
+#else
     u64 hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     u64 t0 = lo - hi_hi;
     if (lo < hi_hi) t0 -= GL_EPS;
@@ -57,6 +85,7 @@ GL_HD u64 gl_reduce128_nc(u64 lo, u64 hi) {
     u64 r = t0 + t1;
     if (r < t1) r += GL_EPS;
     return r;
+#endif
 }
 GL_HD u64 gl_mul_nc(u64 a, u64 b) { u64 lo, hi; gl_mul_wide(a, b, lo, hi); return gl_reduce128_nc(lo, hi); }
 GL_HD u64 gl_mul(u64 a, u64 b) { return gl_canon(gl_mul_nc(a, b)); }

@@ -10,62 +10,70 @@
 
 #define MK_THREADS 128
 
+// state of thread t lives in shared memory at sm[i * MK_THREADS + t], i < 12
+#define ST(i) sm[(i) * MK_THREADS + threadIdx.x]
 __global__ void __launch_bounds__(MK_THREADS) k_leaves_colmajor(const u64 *__restrict__ data, size_t cols, size_t L, u64 *__restrict__ digests) {
+    __shared__ u64 sm[12 * MK_THREADS];
     size_t leaf = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (leaf >= L) return;
-    u64 s[12];
+    const bool active = leaf < L;
+    if (!active) leaf = L - 1;
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (int i = 0; i < 12; i++) ST(i) = 0;
     if (cols <= 4) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) if ((size_t)c < cols) s[c] = data[c * L + leaf];
+        for (size_t c = 0; c < cols; c++) ST(c) = data[c * L + leaf];
     } else {
-        size_t c = 0;
-        for (; c + 8 <= cols; c += 8) {
+        for (size_t c = 0; c < cols; c += 8) {
+            u64 v[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) s[j] = __ldg(data + (c + j) * L + leaf);
-            poseidon_permute(s);
-        }
-        if (c < cols) {
+            for (int j = 0; j < 8; j++) v[j] = (c + j < cols) ? __ldg(data + (c + j) * L + leaf) : 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) if (c + j < cols) s[j] = __ldg(data + (c + j) * L + leaf);
-            poseidon_permute(s);
+            for (int j = 0; j < 8; j++) if (c + j < cols) ST(j) = v[j];
+            poseidon_permute_smem(&ST(0), MK_THREADS);
         }
     }
-    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(digests + 4 * leaf);
-    o[0] = make_ulonglong2(s[0], s[1]); o[1] = make_ulonglong2(s[2], s[3]);
+    if (active) {
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(digests + 4 * leaf);
+        o[0] = make_ulonglong2(ST(0), ST(1)); o[1] = make_ulonglong2(ST(2), ST(3));
+    }
 }
 
 __global__ void __launch_bounds__(MK_THREADS) k_leaves_rowmajor(const u64 *__restrict__ data, size_t width, size_t L, u64 *__restrict__ digests) {
+    __shared__ u64 sm[12 * MK_THREADS];
     size_t leaf = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (leaf >= L) return;
+    const bool active = leaf < L;
+    if (!active) leaf = L - 1;
     const u64 *row = data + leaf * width;
-    u64 s[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (int i = 0; i < 12; i++) ST(i) = 0;
     if (width <= 4) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) if ((size_t)c < width) s[c] = row[c];
+        for (size_t c = 0; c < width; c++) ST(c) = row[c];
     } else {
         for (size_t c = 0; c < width; c += 8) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) if (c + j < width) s[j] = row[c + j];
-            poseidon_permute(s);
+            for (int j = 0; j < 8; j++) if (c + j < width) ST(j) = row[c + j];
+            poseidon_permute_smem(&ST(0), MK_THREADS);
         }
     }
-    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(digests + 4 * leaf);
-    o[0] = make_ulonglong2(s[0], s[1]); o[1] = make_ulonglong2(s[2], s[3]);
+    if (active) {
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(digests + 4 * leaf);
+        o[0] = make_ulonglong2(ST(0), ST(1)); o[1] = make_ulonglong2(ST(2), ST(3));
+    }
 }
 
 __global__ void __launch_bounds__(MK_THREADS) k_merkle_level(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n_out) {
+    __shared__ u64 sm[12 * MK_THREADS];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
+    const bool active = i < n_out;
+    if (!active) i = n_out - 1;
     const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(in + 8 * i);
     ulonglong2 a = p[0], b = p[1], c = p[2], d = p[3];
-    u64 s[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
-    poseidon_permute(s);
-    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + 4 * i);
-    o[0] = make_ulonglong2(s[0], s[1]); o[1] = make_ulonglong2(s[2], s[3]);
+    ST(0) = a.x; ST(1) = a.y; ST(2) = b.x; ST(3) = b.y; ST(4) = c.x; ST(5) = c.y; ST(6) = d.x; ST(7) = d.y;
+    ST(8) = 0; ST(9) = 0; ST(10) = 0; ST(11) = 0;
+    poseidon_permute_smem(&ST(0), MK_THREADS);
+    if (active) {
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + 4 * i);
+        o[0] = make_ulonglong2(ST(0), ST(1)); o[1] = make_ulonglong2(ST(2), ST(3));
+    }
 }
 
 void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digests, cudaStream_t st) {

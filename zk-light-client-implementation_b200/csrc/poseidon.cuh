@@ -50,23 +50,57 @@ GL_HD u64 poseidon_reduce96(u64 lo, u64 hi) {
     return r2;
 }
 
-// MDS: out[r] = sum_i circ[i] * s[(i+r)%12] + 8*s[0]*[r==0]; circ = [17,15,41,16,2,28,13,13,39,18,34,20]
-GL_HD void poseidon_mds(u64 s[12]) {
-    const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    u32 lo[12], hi[12];
+// MDS: out[r] = sum_i circ[i] * s[(i+r)%12] + 8*s[0]*[r==0]; circ = [17,15,41,16,2,28,13,13,39,18,34,20].
+// The circulant is a length-12 cyclic convolution; split indices mod 3, take a length-4 real FFT of every class and the
+// convolution becomes three 3x3 "twisted" products whose constants are all powers of two for this matrix:
+//   k=0 (Y=1):   (64, 128, 64)      k=2 (Y=-1): (-4, -32, 8)      k=1 (Y=-i): (4-2i, -8+2i, 32+2i)
+// so the whole layer is adds and shifts on signed 64-bit integers (no multiplier).  Run separately on the low and the
+// high 32-bit halves of the state (|intermediates| < 2^46), then recombine lo + hi*2^32 and reduce.
+typedef long long i64;
+GL_HD void poseidon_mds_half(const i64 x[12], i64 y[12]) {
+    i64 U0[3], U2[3], Ur[3], Ui[3];
 #pragma unroll
-    for (int i = 0; i < 12; i++) { lo[i] = (u32)s[i]; hi[i] = (u32)(s[i] >> 32); }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        u64 al = 0, ah = 0;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al += (u64)lo[(i + r) % 12] * C[i];
-            ah += (u64)hi[(i + r) % 12] * C[i];
-        }
-        if (r == 0) { al += (u64)lo[0] * 8u; ah += (u64)hi[0] * 8u; }
-        s[r] = poseidon_reduce96(al, ah);
+    for (int r = 0; r < 3; r++) {
+        i64 t0 = x[r] + x[r + 6], t1 = x[r] - x[r + 6], t2 = x[r + 3] + x[r + 9], t3 = x[r + 3] - x[r + 9];
+        U0[r] = t0 + t2; U2[r] = t0 - t2; Ur[r] = t1; Ui[r] = -t3;
     }
+    const i64 S = U0[0] + U0[1] + U0[2];
+    i64 b0[3] = {(S + U0[2]) << 4, (S + U0[0]) << 4, (S + U0[1]) << 4};
+    i64 b2[3] = {(U2[2] << 3) - U2[0] - (U2[1] << 1), -U2[1] - (U2[0] << 3) - (U2[2] << 1), (U2[0] << 1) - U2[2] - (U2[1] << 3)};
+    // (K/2) * U with K0/2 = 2-i, K1/2 = -4+i, K2/2 = 16+i
+#define K0RE(b) ((Ur[b] << 1) + Ui[b])
+#define K0IM(b) ((Ui[b] << 1) - Ur[b])
+#define K1RE(b) (-(Ur[b] << 2) - Ui[b])
+#define K1IM(b) (Ur[b] - (Ui[b] << 2))
+#define K2RE(b) ((Ur[b] << 4) - Ui[b])
+#define K2IM(b) ((Ui[b] << 4) + Ur[b])
+    // w*(u+vi) = v - ui  (w = -i)
+    i64 Wre[3], Wim[3];
+    { i64 ar = K1RE(2) + K2RE(1), ai = K1IM(2) + K2IM(1); Wre[0] = K0RE(0) + ai; Wim[0] = K0IM(0) - ar; }
+    { i64 ar = K2RE(2), ai = K2IM(2); Wre[1] = K0RE(1) + K1RE(0) + ai; Wim[1] = K0IM(1) + K1IM(0) - ar; }
+    Wre[2] = K0RE(2) + K1RE(1) + K2RE(0); Wim[2] = K0IM(2) + K1IM(1) + K2IM(0);
+#undef K0RE
+#undef K0IM
+#undef K1RE
+#undef K1IM
+#undef K2RE
+#undef K2IM
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        i64 s = b0[t] + b2[t], d = b0[t] - b2[t];
+        y[t] = s + Wre[t]; y[t + 6] = s - Wre[t]; y[t + 3] = d - Wim[t]; y[t + 9] = d + Wim[t];
+    }
+}
+
+GL_HD void poseidon_mds(u64 s[12]) {
+    i64 lo[12], hi[12], yl[12], yh[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { lo[i] = (i64)(u32)s[i]; hi[i] = (i64)(s[i] >> 32); }
+    poseidon_mds_half(lo, yl);
+    poseidon_mds_half(hi, yh);
+    yl[0] += lo[0] << 3; yh[0] += hi[0] << 3;          // diagonal term 8*s[0]
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = poseidon_reduce96((u64)yl[r], (u64)yh[r]);
 }
 
 GL_HD void poseidon_full_rounds(u64 s[12], int rc_off) {
@@ -86,10 +120,14 @@ GL_HD void poseidon_full_rounds(u64 s[12], int rc_off) {
 struct acc192 { u64 lo, hi; u32 top; };
 GL_HD void acc192_mad(acc192 &A, u64 a, u64 b) {
     u64 lo, hi; gl_mul_wide(a, b, lo, hi);
+#ifdef __CUDA_ARCH__
+    asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(A.lo), "+l"(A.hi), "+r"(A.top) : "l"(lo), "l"(hi));
+#else
     u64 nl = A.lo + lo; u64 c = nl < lo;
     u64 nh = A.hi + hi; u32 c2 = nh < hi;
     u64 nh2 = nh + c; c2 += nh2 < c;
     A.lo = nl; A.hi = nh2; A.top += c2;
+#endif
 }
 GL_HD u64 acc192_reduce(const acc192 &A) {
     // top * 2^128 : 2^128 = 2^64 * 2^64 == EPS * EPS == 2^64 - 2*2^32 + 1 == (2^32-1) - 2^33 + 2 = -2^32 (mod p)
@@ -140,6 +178,50 @@ GL_HD void poseidon_two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
     poseidon_permute(s);
     out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; out[3] = s[3];
 }
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------
+// Compact device permutation.  ncu on the first version (state in registers, everything unrolled: ~15k SASS
+// instructions per kernel) showed issue-slot utilisation of 35 % with "no_instruction" as the dominant stall: the
+// instruction stream did not fit the SM's instruction caches.  This version keeps the 12-word state in SHARED memory
+// (element-major: word i of thread t at st[i * stride], conflict-free) so that the S-box layer is a rolled loop and the
+// 30 rounds share one copy of the (unrolled, shift/add-only) MDS code: ~1.3k instructions total.  Partial rounds use
+// the textbook form (S-box on word 0, all 12 round constants, full MDS) because with the multiplier-free MDS that is
+// cheaper than the "fast" sparse-matrix form (23 modmuls) and needs no extra tables.  Same permutation, bit-exact.
+// ---------------------------------------------------------------------------------------------------------------
+static __device__ __noinline__ void poseidon_permute_smem(u64 *st, const int stride) {
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        const u64 *rc = d_POSEIDON_RC + 12 * r;
+        u64 s[12];
+        if (full) {
+#pragma unroll 2
+            for (int i = 0; i < 12; i++) {
+                u64 c = rc[i];
+                u64 x = st[i * stride] + c;
+                if (x < c) x += GL_EPS;
+                st[i * stride] = poseidon_sbox(x);
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = st[i * stride];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                u64 c = rc[i];
+                u64 x = st[i * stride] + c;
+                if (x < c) x += GL_EPS;
+                s[i] = x;
+            }
+            s[0] = poseidon_sbox(s[0]);
+        }
+        poseidon_mds(s);
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i * stride] = s[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i * stride] = gl_canon(st[i * stride]);
+}
+#endif
 
 // host-side sponge helpers (used by the challenger / public-input hash)
 inline void poseidon_hash_no_pad_host(const u64 *in, size_t n, u64 out[4]) {
