@@ -66,9 +66,13 @@ __device__ __forceinline__ alg2 alg_mul(alg2 x, alg2 y) {
 __device__ __forceinline__ alg2 alg_scalar(u64 s, alg2 x) { return A2(gl_mul(s, x.a), gl_mul(s, x.b)); }
 __device__ __forceinline__ alg2 W2(const Wires &w, u32 i) { return A2(w[i], w[i + 1]); }
 
+// x(x-1)(x-2)(x-3) = t(t+2) with t = x(x-3): two multiplications
 __device__ __forceinline__ u64 range_prod4(u64 x) {
-    u64 p = gl_mul(x, gl_sub(x, 1)); p = gl_mul(p, gl_sub(x, 2)); return gl_mul(p, gl_sub(x, 3));
+    u64 t = gl_mul(x, gl_sub(x, 3));
+    return gl_mul(t, gl_add(t, 2));
 }
+__device__ __forceinline__ u64 gl_dbl(u64 x) { return gl_add(x, x); }
+__device__ __forceinline__ u64 gl_x4(u64 x) { return gl_dbl(gl_dbl(x)); }
 __device__ __forceinline__ u64 range_prod2(u64 x) { return gl_mul(x, gl_sub(x, 1)); }
 __device__ __forceinline__ u64 range_prod_n(u64 x, int n) { u64 p = 1; for (int k = 0; k < n; k++) p = gl_mul(p, gl_sub(x, (u64)k)); return p; }
 __device__ __forceinline__ u64 sbox7c(u64 x) { return gl_canon(poseidon_sbox(x)); }
@@ -79,68 +83,53 @@ __device__ __forceinline__ void mds_canon(u64 s[12]) {
     for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
 }
 
-static __device__ __noinline__ void eval_poseidon_gate(const Wires &w, ConstraintSink &sink) {
-    u64 swap = w[24];
-    sink.push(gl_mul(swap, gl_sub(swap, 1)));
-    u64 st[12];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
-        sink.push(gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d));
-        st[i] = gl_add(lhs, d); st[i + 4] = gl_sub(rhs, d);
-    }
-#pragma unroll
-    for (int i = 8; i < 12; i++) st[i] = w[i];
-    int rc = 0;
-    for (int r = 0; r < 4; r++, rc++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            u64 x = gl_add(st[i], d_POSEIDON_RC[12 * rc + i]);
-            if (r != 0) { u64 sin = w[29 + 12 * (r - 1) + i]; sink.push(gl_sub(x, sin)); x = sin; }
-            st[i] = sbox7c(x);
-        }
-        mds_canon(st);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], d_POSEIDON_FP_FIRST_RC[i]);
+// PoseidonGate (poseidon_gate.go:92-181) evaluated with the compact permutation structure: the state lives in shared
+// memory, the S-box layer is a rolled loop, all 30 rounds share one MDS.  Partial rounds use the textbook form: the
+// S-box input of round r is (state[0] + RC[12r]) in both the textbook and the "fast" formulation the reference gate
+// is written in (checked in tests/test_gate_parity.py), so every constraint value is identical.
+static __device__ __noinline__ void eval_poseidon_gate_smem(const Wires &w, ConstraintSink &sink, u64 *st, const int stride) {
     {
-        u64 o[12]; o[0] = st[0];
+        u64 swap = w[24];
+        sink.push(gl_mul(swap, gl_sub(swap, 1)));
 #pragma unroll
-        for (int d = 1; d < 12; d++) {
-            acc192 A = {0, 0, 0};
-#pragma unroll
-            for (int r = 1; r < 12; r++) acc192_mad(A, st[r], d_POSEIDON_FP_INIT[11 * (r - 1) + (d - 1)]);
-            o[d] = acc192_reduce(A);
+        for (int i = 0; i < 4; i++) {
+            u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
+            sink.push(gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), d));
+            st[i * stride] = gl_add(lhs, d); st[(i + 4) * stride] = gl_sub(rhs, d);
         }
 #pragma unroll
-        for (int i = 0; i < 12; i++) st[i] = o[i];
+        for (int i = 8; i < 12; i++) st[i * stride] = w[i];
     }
-    for (int r = 0; r < 22; r++) {
-        u64 sin = w[65 + r];
-        sink.push(gl_sub(st[0], sin));
-        u64 x = sbox7c(sin);
-        if (r != 21) x = gl_add(x, d_POSEIDON_FP_RC[r]);
-        acc192 A = {0, 0, 0};
-        acc192_mad(A, x, 25);
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        const u64 *rc = d_POSEIDON_RC + 12 * r;
+        u64 s[12];
+        if (full) {
+            const int wbase = (r < 4) ? 29 + 12 * (r - 1) : 87 + 12 * (r - 26);
+            for (int i = 0; i < 12; i++) {
+                u64 x = gl_add(gl_canon(st[i * stride]), rc[i]);
+                if (r != 0) { u64 sin = w[wbase + i]; sink.push(gl_sub(x, sin)); x = sin; }
+                st[i * stride] = poseidon_sbox(x);
+            }
 #pragma unroll
-        for (int i = 1; i < 12; i++) acc192_mad(A, st[i], d_POSEIDON_FP_W_HATS[11 * r + i - 1]);
+            for (int i = 0; i < 12; i++) s[i] = st[i * stride];
+        } else {
 #pragma unroll
-        for (int i = 1; i < 12; i++) st[i] = gl_add(st[i], gl_mul(x, d_POSEIDON_FP_VS[11 * r + i - 1]));
-        st[0] = acc192_reduce(A);
-    }
-    rc += 22;
-    for (int r = 0; r < 4; r++, rc++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            u64 x = gl_add(st[i], d_POSEIDON_RC[12 * rc + i]);
-            u64 sin = w[87 + 12 * r + i];
-            sink.push(gl_sub(x, sin));
-            st[i] = sbox7c(sin);
+            for (int i = 0; i < 12; i++) {
+                u64 c = rc[i];
+                u64 x = st[i * stride] + c;
+                if (x < c) x += GL_EPS;
+                s[i] = x;
+            }
+            u64 sin = w[65 + (r - 4)];
+            sink.push(gl_sub(gl_canon(s[0]), sin));
+            s[0] = poseidon_sbox(sin);
         }
-        mds_canon(st);
-    }
+        poseidon_mds(s);
 #pragma unroll
-    for (int i = 0; i < 12; i++) sink.push(gl_sub(st[i], w[12 + i]));
+        for (int i = 0; i < 12; i++) st[i * stride] = s[i];
+    }
+    for (int i = 0; i < 12; i++) sink.push(gl_sub(gl_canon(st[i * stride]), w[12 + i]));
 }
 
 static __device__ __noinline__ void eval_coset_interpolation(const GateDesc &g, const Wires &w, const u64 *weights, ConstraintSink &sink) {
@@ -170,10 +159,12 @@ static __device__ __noinline__ void eval_coset_interpolation(const GateDesc &g, 
     alg2 d = alg_sub(W2(w, 1 + 2 * np + 2), ev); sink.push(d.a); sink.push(d.b);
 }
 
-// consts: constant columns AFTER the selector prefix
+// consts: constant columns AFTER the selector prefix.  KIND is a compile-time constant: every gate kind gets its own
+// small kernel (k_gate<KIND> in plonk.cu) -- a monolithic all-gates kernel (26 k instructions) was instruction-fetch bound.
+template <int KIND>
 __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, const Wires &w, const u64 *pi_hash,
-                                          const u64 *extra, ConstraintSink &sink) {
-    switch (g.kind) {
+                                          const u64 *extra, ConstraintSink &sink, u64 *smem_state, int smem_stride) {
+    switch (KIND) {
     case G_NOOP: break;
     case G_CONSTANT: for (u32 i = 0; i < g.p[0]; i++) sink.push(gl_sub(c[i], w[i])); break;
     case G_PUBLIC_INPUT: for (u32 i = 0; i < 4; i++) sink.push(gl_sub(w[i], pi_hash[i])); break;
@@ -203,7 +194,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
         for (u32 i = 0; i < n; i++) sink.push(base == 2 ? range_prod2(w[1 + i]) : range_prod_n(w[1 + i], (int)base));
         break; }
     case G_REDUCING: case G_REDUCING_EXT: {
-        const u32 n = g.p[0]; const bool ext = g.kind == G_REDUCING_EXT;
+        const u32 n = g.p[0]; const bool ext = KIND == G_REDUCING_EXT;
         const u32 start_accs = 6 + (ext ? 2 * n : n);
         alg2 alpha = W2(w, 2), acc = W2(w, 4);
         for (u32 i = 0; i < n; i++) {
@@ -245,7 +236,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
             alg2 d = alg_sub(W2(w, 24 + 2 * r), acc); sink.push(d.a); sink.push(d.b);
         }
         break; }
-    case G_POSEIDON: eval_poseidon_gate(w, sink); break;
+    case G_POSEIDON: eval_poseidon_gate_smem(w, sink, smem_state, smem_stride); break;
     case G_COSET_INTERPOLATION: eval_coset_interpolation(g, w, extra + g.extra_off, sink); break;
     case G_U32_ARITHMETIC: {
         const u32 n = g.p[0];
@@ -258,7 +249,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
             for (int j = 31; j >= 0; j--) {
                 u64 limb = w[6 * n + 32 * i + j];
                 sink.push(range_prod4(limb));
-                if (j < 16) cl = gl_add(gl_mul(cl, 4), limb); else ch = gl_add(gl_mul(ch, 4), limb);
+                if (j < 16) cl = gl_add(gl_x4(cl), limb); else ch = gl_add(gl_x4(ch), limb);
             }
             sink.push(gl_sub(cl, lo)); sink.push(gl_sub(ch, hi));
         }
@@ -274,7 +265,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
             for (int j = 17; j >= 0; j--) {
                 u64 limb = w[r * n + 18 * i + j];
                 sink.push(range_prod4(limb));
-                if (j < 16) cr = gl_add(gl_mul(cr, 4), limb); else cc = gl_add(gl_mul(cc, 4), limb);
+                if (j < 16) cr = gl_add(gl_x4(cr), limb); else cc = gl_add(gl_x4(cc), limb);
             }
             sink.push(gl_sub(cr, res)); sink.push(gl_sub(cc, carry));
         }
@@ -285,7 +276,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
             u64 x = w[5 * i], y = w[5 * i + 1], bi = w[5 * i + 2], res = w[5 * i + 3], bo = w[5 * i + 4];
             sink.push(gl_sub(res, gl_add(gl_sub(gl_sub(x, y), bi), gl_mul(1ULL << 32, bo))));
             u64 cl = 0;
-            for (int j = 15; j >= 0; j--) { u64 limb = w[5 * n + 16 * i + j]; sink.push(range_prod4(limb)); cl = gl_add(gl_mul(cl, 4), limb); }
+            for (int j = 15; j >= 0; j--) { u64 limb = w[5 * n + 16 * i + j]; sink.push(range_prod4(limb)); cl = gl_add(gl_x4(cl), limb); }
             sink.push(gl_sub(cl, res));
             sink.push(gl_mul(bo, gl_sub(1, bo)));
         }
@@ -294,7 +285,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
         const u32 n = g.p[0];
         for (u32 i = 0; i < n; i++) {
             u64 acc = 0;
-            for (int j = 15; j >= 0; j--) acc = gl_add(gl_mul(acc, 4), w[n + 16 * i + j]);
+            for (int j = 15; j >= 0; j--) acc = gl_add(gl_x4(acc), w[n + 16 * i + j]);
             sink.push(gl_sub(acc, w[i]));
             for (int j = 0; j < 16; j++) sink.push(range_prod4(w[n + 16 * i + j]));
         }
@@ -303,13 +294,13 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
         const u32 n = g.p[0];
         for (u32 i = 0; i < n; i++) {
             u64 cx = 0, ci = 0;
-            for (int j = 0; j < 32; j++) { u64 b = w[2 * n + 32 * i + j]; cx = gl_add(gl_add(cx, cx), b); ci = gl_add(gl_mul(ci, 4), b); }
+            for (int j = 0; j < 32; j++) { u64 b = w[2 * n + 32 * i + j]; cx = gl_add(gl_dbl(cx), b); ci = gl_add(gl_x4(ci), b); }
             sink.push(gl_sub(cx, w[2 * i])); sink.push(gl_sub(ci, w[2 * i + 1]));
             for (int j = 0; j < 32; j++) sink.push(range_prod2(w[2 * n + 32 * i + j]));
         }
         break; }
     case G_UNINTERLEAVE_U32: case G_UNINTERLEAVE_B32: {
-        const u32 n = g.p[0]; const bool b32 = g.kind == G_UNINTERLEAVE_B32;
+        const u32 n = g.p[0]; const bool b32 = KIND == G_UNINTERLEAVE_B32;
         for (u32 i = 0; i < n; i++) {
             u64 ci = 0, ce = 0, co = 0;
             for (int j = 0; j < 64; j++) {

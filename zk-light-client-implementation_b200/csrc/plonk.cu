@@ -116,73 +116,107 @@ void launch_partial_products(const u64 *d_wires, const u64 *d_sigmas, const u64 
 // =====================================================================================================
 // 2. quotient
 // =====================================================================================================
-__global__ void __launch_bounds__(128) k_quotient(QuotientArgs a) {
+// --- 2a. permutation terms: acc[k][pos] = sum over the L_0 and partial-product checks of term * alpha_k^idx ---
+__global__ void __launch_bounds__(128) k_quotient_perm(QuotientArgs a) {
     const int L = a.log_n + a.rate_bits;
     const size_t N = size_t(1) << L;
     size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (pos >= N) return;
     const u32 i = bitrev32((u32)pos, L);                       // natural point index
     const u32 rmask = (1u << a.rate_bits) - 1;
-    // x = g * w_N^i
     u64 x;
     { size_t h = N >> 1; u64 wi = (i < h) ? __ldg(a.tw_fwd + h + i) : gl_neg(__ldg(a.tw_fwd + h + (i - h))); x = gl_mul(GL_GEN, wi); }
     Wires cs = {a.cs_lde, N, pos}, w = {a.wires_lde, N, pos}, zs = {a.zs_lde, N, pos};
     const size_t pos_next = bitrev32((u32)((i + (1u << a.rate_bits)) & (N - 1)), L);
     Wires zs_next = {a.zs_lde, N, pos_next};
     const u32 nch = a.num_challenges, npp = a.npp;
-    const u32 gate_off = nch + nch * (npp + 1);                // index of the first gate constraint among the vanishing terms
-
     acc192 tot[MAX_CHALLENGES];
 #pragma unroll
     for (int k = 0; k < MAX_CHALLENGES; k++) { tot[k].lo = 0; tot[k].hi = 0; tot[k].top = 0; }
-
-    // ---- L_0(x) (Z(x) - 1) and the partial-product checks ----
-    {
-        u64 l0 = gl_mul(a.zh_ev[i & rmask], gl_mul(a.n_inv, gl_inv(gl_sub(x, 1))));
-        for (u32 c = 0; c < nch; c++) {
-            u64 z = zs[c];
-            u64 t = gl_mul(l0, gl_sub(z, 1));
-            for (u32 k = 0; k < nch; k++) acc192_mad(tot[k], t, __ldg(a.apow + k * a.apow_stride + c));
-            u64 prev = z;
-            for (u32 kk = 0; kk <= npp; kk++) {
-                u64 num = 1, den = 1;
-                for (u32 j = kk * a.qdf; j < (kk + 1) * a.qdf && j < a.num_routed; j++) {
-                    u64 t0 = gl_add(w[j], a.gammas[c]);
-                    num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j), x))));
-                    den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], cs[a.num_constants + j])));
-                }
-                u64 next = kk < npp ? zs[nch + c * npp + kk] : zs_next[c];
-                u64 term = gl_sub(gl_mul(prev, num), gl_mul(next, den));
-                u32 tidx = nch + c * (npp + 1) + kk;
-                for (u32 k = 0; k < nch; k++) acc192_mad(tot[k], term, __ldg(a.apow + k * a.apow_stride + tidx));
-                prev = next;
+    u64 l0 = gl_mul(a.zh_ev[i & rmask], gl_mul(a.n_inv, gl_inv(gl_sub(x, 1))));
+    for (u32 c = 0; c < nch; c++) {
+        u64 z = zs[c];
+        u64 t = gl_mul(l0, gl_sub(z, 1));
+        for (u32 k = 0; k < nch; k++) acc192_mad(tot[k], t, __ldg(a.apow + k * a.apow_stride + c));
+        u64 prev = z;
+        for (u32 kk = 0; kk <= npp; kk++) {
+            u64 num = 1, den = 1;
+            for (u32 j = kk * a.qdf; j < (kk + 1) * a.qdf && j < a.num_routed; j++) {
+                u64 t0 = gl_add(w[j], a.gammas[c]);
+                num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j), x))));
+                den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], cs[a.num_constants + j])));
             }
+            u64 next = kk < npp ? zs[nch + c * npp + kk] : zs_next[c];
+            u64 term = gl_sub(gl_mul(prev, num), gl_mul(next, den));
+            u32 tidx = nch + c * (npp + 1) + kk;
+            for (u32 k = 0; k < nch; k++) acc192_mad(tot[k], term, __ldg(a.apow + k * a.apow_stride + tidx));
+            prev = next;
         }
     }
-    // ---- gates ----
-    ConstraintSink sink; sink.apow = a.apow; sink.apow_stride = a.apow_stride;
+    for (u32 k = 0; k < nch; k++) a.acc[(size_t)k * N + pos] = acc192_reduce(tot[k]);
+}
+
+// --- 2b. one kernel per gate kind: acc[k][pos] += alpha_k^{gate_off} * filter_g(x) * sum_i c_i alpha_k^i ---
+template <int KIND>
+__global__ void __launch_bounds__(128) k_gate(QuotientArgs a, GateDesc g) {
+    __shared__ u64 sm[KIND == G_POSEIDON ? 12 * 128 : 1];
+    const int L = a.log_n + a.rate_bits;
+    const size_t N = size_t(1) << L;
+    size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const bool active = pos < N;
+    if (!active) pos = N - 1;
+    Wires cs = {a.cs_lde, N, pos}, w = {a.wires_lde, N, pos};
     Wires gc = {a.cs_lde + (size_t)a.num_selectors * N, N, pos};
-    u64 gsum[MAX_CHALLENGES] = {0, 0};
-    for (u32 gi = 0; gi < a.num_gates; gi++) {
-        const GateDesc g = a.gates[gi];
-        if (g.num_constraints == 0) continue;
-        u64 sel = cs[g.selector_index], filt = 1;
-        for (u32 r = g.group_start; r < g.group_end; r++) if (r != g.row) filt = gl_mul(filt, gl_sub((u64)r, sel));
-        if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
-        sink.reset();
-        eval_gate(g, gc, w, a.pi_hash, a.extra, sink);
-        for (u32 k = 0; k < nch; k++) gsum[k] = gl_add(gsum[k], gl_mul(filt, sink.result(k)));
-    }
-    for (u32 k = 0; k < nch; k++) {
-        // gate constraint i carries alpha^{gate_off + i}: multiply the gate sum by alpha^{gate_off}
-        acc192_mad(tot[k], gsum[k], __ldg(a.apow + k * a.apow_stride + gate_off));
-        u64 v = gl_mul(acc192_reduce(tot[k]), a.zh_inv[i & rmask]);
-        a.out[(size_t)k * N + i] = v;
+    u64 sel = cs[g.selector_index], filt = 1;
+    for (u32 r = g.group_start; r < g.group_end; r++) if (r != g.row) filt = gl_mul(filt, gl_sub((u64)r, sel));
+    if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
+    ConstraintSink sink; sink.apow = a.apow; sink.apow_stride = a.apow_stride;
+    sink.reset();
+    eval_gate<KIND>(g, gc, w, a.pi_hash, a.extra, sink, &sm[KIND == G_POSEIDON ? threadIdx.x : 0], 128);
+    if (!active) return;
+    const u32 gate_off = a.num_challenges + a.num_challenges * (a.npp + 1);
+    for (u32 k = 0; k < a.num_challenges; k++) {
+        u64 v = gl_mul(gl_mul(filt, sink.result(k)), __ldg(a.apow + k * a.apow_stride + gate_off));
+        u64 *p = a.acc + (size_t)k * N + pos;
+        *p = gl_add(*p, v);
     }
 }
-void launch_quotient(const QuotientArgs &a, cudaStream_t st) {
+
+// --- 2c. out[k][natural i] = acc[k][pos] / Z_H(x) ---
+__global__ void k_quotient_finish(QuotientArgs a) {
+    const int L = a.log_n + a.rate_bits;
+    const size_t N = size_t(1) << L;
+    size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    const u32 i = bitrev32((u32)pos, L);
+    const u32 rmask = (1u << a.rate_bits) - 1;
+    for (u32 k = 0; k < a.num_challenges; k++) a.out[(size_t)k * N + i] = gl_mul(a.acc[(size_t)k * N + pos], a.zh_inv[i & rmask]);
+}
+
+template <int KIND> static void launch_gate(const QuotientArgs &a, const GateDesc &g, unsigned blocks, cudaStream_t st) {
+    k_gate<KIND><<<blocks, 128, 0, st>>>(a, g);
+    LAUNCHED(1);
+}
+
+void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, cudaStream_t st) {
     size_t N = size_t(1) << (a.log_n + a.rate_bits);
-    k_quotient<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    unsigned blocks = (unsigned)((N + 127) / 128);
+    k_quotient_perm<<<blocks, 128, 0, st>>>(a);
+    LAUNCHED(1);
+    for (u32 gi = 0; gi < a.num_gates; gi++) {
+        const GateDesc &g = h_gates[gi];
+        if (g.num_constraints == 0) continue;
+        switch (g.kind) {
+#define GK(K) case K: launch_gate<K>(a, g, blocks, st); break;
+        GK(G_CONSTANT) GK(G_PUBLIC_INPUT) GK(G_ARITHMETIC) GK(G_ARITHMETIC_EXT) GK(G_MUL_EXT) GK(G_BASE_SUM) GK(G_REDUCING)
+        GK(G_REDUCING_EXT) GK(G_RANDOM_ACCESS) GK(G_POSEIDON_MDS) GK(G_POSEIDON) GK(G_COSET_INTERPOLATION) GK(G_U32_ARITHMETIC)
+        GK(G_U32_ADD_MANY) GK(G_U32_SUBTRACTION) GK(G_U32_RANGE_CHECK) GK(G_U32_INTERLEAVE) GK(G_UNINTERLEAVE_U32)
+        GK(G_UNINTERLEAVE_B32) GK(G_COMPARISON)
+#undef GK
+        default: throw CudaErr{cudaErrorInvalidValue, __FILE__, __LINE__};
+        }
+    }
+    k_quotient_finish<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a);
     LAUNCHED(1);
 }
 

@@ -6,6 +6,7 @@
 struct QuotientArgs {
     const u64 *cs_lde, *wires_lde, *zs_lde;      // [cols][N] column-major, bit-reversed rows
     u64 *out;                                    // [num_challenges][N], written at the NATURAL point index
+    u64 *acc;                                    // [num_challenges][N] scratch accumulator in storage (bit-reversed) order
     const GateDesc *gates; const u64 *extra; const u64 *k_is;
     const u64 *apow;                             // [MAX_CHALLENGES][apow_stride] alpha powers
     const u64 *tw_fwd;                           // twiddle table (for x = g * w_N^i)
@@ -22,7 +23,7 @@ void launch_partial_products(const u64 *d_wires, const u64 *d_sigmas, const u64 
                              u32 num_challenges, const u64 *betas, const u64 *gammas, const u64 *tw_fwd,
                              u64 *d_zs_pp /*[nch*(1+npp)][n]*/, u64 *d_scratch /* >= nch*(npp+2)*n + 4096 u64 */, u64 *d_final_prod /*[nch]*/,
                              cudaStream_t st);
-void launch_quotient(const QuotientArgs &a, cudaStream_t st);
+void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, cudaStream_t st);
 // big[ci][.] (size N, br order, coefficients of the coset-shifted quotient) -> chunk polys coeffs_br[ci*qdf + m][n]
 void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 num_challenges, cudaStream_t st);
 // table[q] = base^{bitrev(q)} (ext), q < 2^L ; pows2[b] = base^(2^b)

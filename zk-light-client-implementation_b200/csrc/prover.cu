@@ -213,7 +213,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
             for (u32 i = 0; i < (1u << rb); i++) { qa.zh_ev[i] = gl_sub(gl_mul(g_pow_n, x), 1); qa.zh_inv[i] = gl_inv(qa.zh_ev[i]); x = gl_mul(x, wr); }
             qa.n_inv = gl_inv((u64)n % GL_P);
         }
-        { PhaseTimer t(ctx, "quotient"); launch_quotient(qa, st); }
+        qa.acc = q_big;     // scratch until the iNTT overwrites it
+        { PhaseTimer t(ctx, "quotient"); launch_quotient(qa, k->gates.data(), st); }
         // coefficients of Q(gX): DIF inverse NTT natural -> bit-reversed, scaled by 1/N
         { PhaseTimer t(ctx, "quotient_intt"); ntt_dif(ctx->tw, q_vals, N, false, q_big, N, Llog, nch, 0, nullptr, true, gl_inv((u64)N % GL_P), st); }
         // q_vals is free again: reuse as chunk coefficient storage?  keep separate buffers for clarity
