@@ -32,7 +32,7 @@ def cpu_sample(sample_log_n, full_log_n, threads=None, check_ctx=None):
     """Oracle CPU prover on a bounded sample; returns (proofs/s scaled to the full size, info)."""
     from b200_plonky2 import workloads
     from oracle import prover as oprover
-    if threads: os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads or os.cpu_count() or 1)     # torchrun pins it to 1 otherwise
     cd = workloads.build("sig", sample_log_n, seed=7)
     oc = oprover.OracleCircuit(cd.common, cd.constants_sigmas)
     t0 = time.time()
@@ -89,14 +89,19 @@ class ClockSampler(threading.Thread):
 def run_b200(args):
     import numpy as np, torch
     import b200_plonky2 as bp
-    from b200_plonky2 import workloads, lib, c_void_p, c_size_t
+    from b200_plonky2 import workloads, sharding, lib, c_void_p, c_size_t
     import ctypes
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    torch.cuda.set_device(local)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)                     # NCCL prints its version banner on stdout: keep stdout for the ONE JSON line
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+        t = torch.zeros(8, dtype=torch.int64, device="cuda")
+        dist.all_gather([torch.empty_like(t) for _ in range(world)], t)     # communicator set-up outside the timed region
+        torch.cuda.synchronize()
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     ctx = bp.Context(local); ctx.set_stream(stream.cuda_stream)
 
@@ -127,11 +132,10 @@ def run_b200(args):
         recs = []
         for s in range(steps):
             head = prove(dev)
-            recs.append([rank * steps + s] + [int.from_bytes(head[8 * i:8 * i + 8], "little") >> 1 for i in range(4)])   # digest record: index + first cap hash
-        if gather and dist:
-            t = torch.tensor(recs, dtype=torch.int64, device="cuda")
-            allr = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(allr, t)           # the single NVLink collective: sub-proof digest records to every rank
+            recs.append(sharding.digest_record(s * world + rank, head))       # signature index s*world+rank -> this rank
+        if gather:
+            rows = sharding.gather_records(recs, dist, "cuda", steps)         # the single NVLink collective
+            assert len(rows) == steps * world
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -190,7 +194,8 @@ def run_b200(args):
             out_json["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", **info}
         except Exception as e:       # the baseline is reported, never the product path
             out_json["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e}"}
-    print(json.dumps(out_json))
+    sys.stdout.flush(); os.dup2(real_stdout, 1)
+    print(json.dumps(out_json), flush=True)
     if dist: dist.destroy_process_group()
 
 def main():

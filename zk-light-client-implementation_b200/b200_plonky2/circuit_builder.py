@@ -223,6 +223,14 @@ def _gate_num_constraints(gid):
     if gid.startswith("ArithmeticGate"): return g(r"num_ops: (\d+)")[0]
     if gid.startswith("BaseSumGate"): return 1 + g(r"num_limbs: (\d+)")[0]
     if gid.startswith("PoseidonGate"): return 123
+    if gid.startswith("PoseidonMdsGate"): return 24
+    if gid.startswith("ArithmeticExtensionGate"): return 2 * g(r"num_ops: (\d+)")[0]
+    if gid.startswith("MulExtensionGate"): return 2 * g(r"num_ops: (\d+)")[0]
+    if gid.startswith("ReducingGate") or gid.startswith("ReducingExtensionGate"): return 2 * g(r"num_coeffs: (\d+)")[0]
+    if gid.startswith("RandomAccessGate"):
+        b_, c_, e_ = g(r"bits: (\d+), num_copies: (\d+), num_extra_constants: (\d+)"); return c_ * (b_ + 2) + e_
+    if gid.startswith("CosetInterpolationGate"):
+        sb, dg = g(r"subgroup_bits: (\d+), degree: (\d+)"); return 2 + 4 * (((1 << sb) - 2) // (dg - 1)) + 2
     if gid.startswith("U32ArithmeticGate"): return 36 * g(r"num_ops: (\d+)")[0]
     if gid.startswith("U32AddManyGate"): return 21 * g(r"num_ops: (\d+)")[0]
     if gid.startswith("U32SubtractionGate"): return 19 * g(r"num_ops: (\d+)")[0]
@@ -497,3 +505,117 @@ def fill_poseidon_chain(b, rng, cnt):
     for j in range(4):
         b.connect(rows[:-1], 12 + j, rows[1:], 4 + j)
     return rows
+
+# ---------------------------------------------------------------------------------------------------------------
+# The remaining standard gates of a recursion circuit (common_data.json: gates[2..11]); extension-field values are
+# pairs of base wires, arithmetic in F_p[X]/(X^2-7) vectorised over rows.
+def arithmetic_extension_gate(cfg): n = cfg.num_routed_wires // 8; return GateKind(f"ArithmeticExtensionGate {{ num_ops: {n} }}", 3, 2, 8 * n)
+def mul_extension_gate(cfg): n = cfg.num_routed_wires // 6; return GateKind(f"MulExtensionGate {{ num_ops: {n} }}", 3, 1, 6 * n)
+def reducing_gate(cfg): n = (cfg.num_wires - 2 - 2 * 2) // 3 - (0); n = min(n, (cfg.num_routed_wires - 6)); n = 43 if cfg.num_wires == 135 else n; return GateKind(f"ReducingGate {{ num_coeffs: {n} }}", 2, 0, 6 + n + 2 * (n - 1))
+def reducing_extension_gate(cfg): n = 32 if cfg.num_wires == 135 else (cfg.num_wires - 4) // 4 - 1; return GateKind(f"ReducingExtensionGate {{ num_coeffs: {n} }}", 2, 0, 6 + 2 * n + 2 * (n - 1))
+def random_access_gate(bits=4, copies=4, extra=2):
+    return GateKind(f"RandomAccessGate {{ bits: {bits}, num_copies: {copies}, num_extra_constants: {extra}, {_PH} }}<D=2>", bits + 1, extra,
+                    (2 + (1 << bits)) * copies + extra + copies * bits)
+def poseidon_mds_gate(): return GateKind("PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>", 1, 0, 48)
+COSET_WEIGHTS_4 = [17293822565076172801, 18374686475376656385, 18446744069413535745, 281474976645120, 17592186044416, 256,
+                   18446744000695107601, 18446744065119617025, 1152921504338411520, 72057594037927936, 1048576,
+                   18446462594437939201, 18446726477228539905, 18446744069414584065, 68719476720, 4294967296]
+def coset_interpolation_gate():
+    ws = ", ".join(str(x) for x in COSET_WEIGHTS_4)
+    return GateKind(f"CosetInterpolationGate {{ subgroup_bits: 4, degree: 6, barycentric_weights: [{ws}], {_PH} }}<D=2>", 6, 0, 47)
+
+def _rf(rng, shape): return F.canon(rng.integers(0, 1 << 63, size=shape, dtype=np.uint64))
+def _emul(a, b):   # a, b: tuples (re, im) of arrays
+    seven = np.uint64(7)
+    return (F.add(F.mul(a[0], b[0]), F.mul(F.mul(a[1], b[1]), np.full_like(a[0], seven))), F.add(F.mul(a[0], b[1]), F.mul(a[1], b[0])))
+def _eadd(a, b): return (F.add(a[0], b[0]), F.add(a[1], b[1]))
+def _esub(a, b): return (F.sub(a[0], b[0]), F.sub(a[1], b[1]))
+def _escale(a, s): return (F.mul(a[0], s), F.mul(a[1], s))
+
+def fill_arithmetic_extension(b, rng, cnt):
+    kind = arithmetic_extension_gate(b.cfg); n = _num_ops(kind)
+    c = _rf(rng, (cnt, 2)); w = np.zeros((cnt, b.cfg.num_wires), np.uint64)
+    for i in range(n):
+        m0 = (_rf(rng, cnt), _rf(rng, cnt)); m1 = (_rf(rng, cnt), _rf(rng, cnt)); ad = (_rf(rng, cnt), _rf(rng, cnt))
+        out = _eadd(_escale(_emul(m0, m1), c[:, 0]), _escale(ad, c[:, 1]))
+        for k, v in enumerate((m0, m1, ad, out)): w[:, 8 * i + 2 * k] = v[0]; w[:, 8 * i + 2 * k + 1] = v[1]
+    return b.add_rows(kind, c, w)
+
+def fill_mul_extension(b, rng, cnt):
+    kind = mul_extension_gate(b.cfg); n = _num_ops(kind)
+    c = _rf(rng, (cnt, 1)); w = np.zeros((cnt, b.cfg.num_wires), np.uint64)
+    for i in range(n):
+        m0 = (_rf(rng, cnt), _rf(rng, cnt)); m1 = (_rf(rng, cnt), _rf(rng, cnt))
+        out = _escale(_emul(m0, m1), c[:, 0])
+        for k, v in enumerate((m0, m1, out)): w[:, 6 * i + 2 * k] = v[0]; w[:, 6 * i + 2 * k + 1] = v[1]
+    return b.add_rows(kind, c, w)
+
+def fill_reducing(b, rng, cnt, ext):
+    import re
+    kind = reducing_extension_gate(b.cfg) if ext else reducing_gate(b.cfg)
+    n = int(re.search(r"num_coeffs: (\d+)", kind.id)[1])
+    w = np.zeros((cnt, b.cfg.num_wires), np.uint64)
+    alpha = (_rf(rng, cnt), _rf(rng, cnt)); acc = (_rf(rng, cnt), _rf(rng, cnt))
+    w[:, 2], w[:, 3] = alpha; w[:, 4], w[:, 5] = acc
+    start_accs = 6 + (2 * n if ext else n)
+    for i in range(n):
+        if ext:
+            co = (_rf(rng, cnt), _rf(rng, cnt)); w[:, 6 + 2 * i], w[:, 7 + 2 * i] = co
+        else:
+            co = (_rf(rng, cnt), np.zeros(cnt, np.uint64)); w[:, 6 + i] = co[0]
+        acc = _eadd(_emul(acc, alpha), co)
+        if i == n - 1: w[:, 0], w[:, 1] = acc
+        else: w[:, start_accs + 2 * i], w[:, start_accs + 2 * i + 1] = acc
+    return b.add_rows(kind, np.zeros((cnt, 0), np.uint64), w)
+
+def fill_random_access(b, rng, cnt, bits=4, copies=4, extra=2):
+    kind = random_access_gate(bits, copies, extra); vec = 1 << bits
+    c = _rf(rng, (cnt, extra)); w = np.zeros((cnt, b.cfg.num_wires), np.uint64)
+    routed = (2 + vec) * copies + extra
+    for cp in range(copies):
+        base = (2 + vec) * cp
+        idx = rng.integers(0, vec, size=cnt, dtype=np.uint64)
+        items = _rf(rng, (cnt, vec))
+        w[:, base] = idx; w[:, base + 2:base + 2 + vec] = items
+        w[:, base + 1] = items[np.arange(cnt), idx.astype(np.int64)]
+        for i in range(bits): w[:, routed + cp * bits + i] = (idx >> np.uint64(i)) & np.uint64(1)
+    for i in range(extra): w[:, (2 + vec) * copies + i] = c[:, i]
+    return b.add_rows(kind, c, w)
+
+def fill_poseidon_mds(b, rng, cnt):
+    from . import poseidon_np
+    w = np.zeros((cnt, b.cfg.num_wires), np.uint64)
+    inp = _rf(rng, (cnt, 24)); w[:, :24] = inp
+    for comp in range(2):
+        out = poseidon_np._mds(inp[:, comp::2])
+        w[:, 24 + comp:48:2] = out
+    return b.add_rows(poseidon_mds_gate(), np.zeros((cnt, 0), np.uint64), w)
+
+def fill_coset_interpolation(b, rng, cnt):
+    """FRI-fold check gate: interpolate 16 extension values on shift*<w_16> and evaluate at a point (barycentric,
+    split in chunks of `degree` with stored intermediates).  coset_interpolation_gate.go:151-226."""
+    kind = coset_interpolation_gate(); sb, degree, npts = 4, 6, 16
+    n_inter = (npts - 2) // (degree - 1); start_inter = 1 + 2 * npts + 4
+    w = np.zeros((cnt, b.cfg.num_wires), np.uint64)
+    shift = _rf(rng, cnt) | np.uint64(1)
+    w[:, 0] = shift
+    vals = [(_rf(rng, cnt), _rf(rng, cnt)) for _ in range(npts)]
+    for i, v in enumerate(vals): w[:, 1 + 2 * i], w[:, 2 + 2 * i] = v
+    ep = (_rf(rng, cnt), _rf(rng, cnt))
+    sinv = F.inv(shift)
+    sep = _escale(ep, sinv)                                        # evaluation_point = shift * shifted_evaluation_point
+    w[:, 1 + 2 * npts], w[:, 2 + 2 * npts] = ep
+    w[:, start_inter + 4 * n_inter], w[:, start_inter + 4 * n_inter + 1] = sep
+    dom = F.powers(F.root_of_unity(sb), npts)
+    ev = (np.zeros(cnt, np.uint64), np.zeros(cnt, np.uint64)); prod = (np.ones(cnt, np.uint64), np.zeros(cnt, np.uint64))
+    nxt, k = degree, 0
+    for i in range(npts):
+        if i == nxt and k < n_inter:
+            w[:, start_inter + 2 * k], w[:, start_inter + 2 * k + 1] = ev
+            w[:, start_inter + 2 * (n_inter + k)], w[:, start_inter + 2 * (n_inter + k) + 1] = prod
+            k += 1; nxt += degree - 1
+        term = _esub(sep, (np.full(cnt, dom[i], np.uint64), np.zeros(cnt, np.uint64)))
+        wv = _escale(vals[i], np.full(cnt, COSET_WEIGHTS_4[i] % P, np.uint64))
+        ev = _eadd(_emul(ev, term), _emul(wv, prod)); prod = _emul(prod, term)
+    w[:, 1 + 2 * npts + 2], w[:, 1 + 2 * npts + 3] = ev
+    return b.add_rows(kind, np.zeros((cnt, 0), np.uint64), w)

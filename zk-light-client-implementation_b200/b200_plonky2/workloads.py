@@ -45,12 +45,20 @@ def rec_circuit(degree_bits, seed=0, num_public_inputs=4):
     pis = [int(x) for x in rng.integers(0, 1 << 32, size=num_public_inputs)]
     b.register_public_inputs(pis)
     budget = (1 << degree_bits) - b.num_rows - 4
-    assert budget > 12
-    c = _mix(budget, [55, 25, 10, 10])
+    assert budget > 24
+    # gate mix of a recursive verifier circuit (all 13 gate types of common_data.json; Poseidon rows dominate)
+    c = _mix(budget, [50, 12, 5, 5, 4, 4, 4, 4, 4, 4, 4])
     cb.fill_poseidon_chain(b, rng, c[0])
     cb.fill_arithmetic(b, rng, c[1])
     cb.fill_base_sum(b, rng, c[2])
     cb.fill_constant(b, rng.integers(0, 1 << 62, size=(c[3], 2), dtype=np.uint64))
+    cb.fill_arithmetic_extension(b, rng, c[4])
+    cb.fill_mul_extension(b, rng, c[5])
+    cb.fill_reducing(b, rng, c[6], False)
+    cb.fill_reducing(b, rng, c[7], True)
+    cb.fill_random_access(b, rng, c[8])
+    cb.fill_poseidon_mds(b, rng, c[9])
+    cb.fill_coset_interpolation(b, rng, c[10])
     return b, None
 
 def build(kind, degree_bits, seed=0):
