@@ -91,6 +91,42 @@ static void hash_leaf_colmajor(const u64 *base, size_t cols, size_t L, size_t ro
  * down to the cap level (2^cap_height x 4); total 4*(2L - 2^cap_height) u64.  Returns pointer to cap inside digests. */
 size_t orc_merkle_num_u64(int log_L, int cap_height) { return 4 * ((2ULL << log_L) - (1ULL << cap_height)); }
 
+/* hasher: 0 = PoseidonHash (Goldilocks), 1 = PoseidonBN128Hash (oracle/c/bn254.c) */
+void orc_bn254_hash_or_noop_strided(const u64 *in, size_t n, size_t stride, u64 out[4]);
+void orc_bn254_two_to_one(const u64 l[4], const u64 r[4], u64 out[4]);
+
+void orc_merkle_from_digests_h(u64 *digests, int log_L, int cap_height, int hasher) {
+    u64 *cur = digests;
+    for (int lv = log_L; lv > cap_height; lv--) {
+        size_t n = 1ULL << lv;
+        u64 *nxt = cur + 4 * n;
+        #pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n / 2; i++) {
+            if (hasher) orc_bn254_two_to_one(cur + 8 * i, cur + 8 * i + 4, nxt + 4 * i);
+            else orc_two_to_one(cur + 8 * i, cur + 8 * i + 4, nxt + 4 * i);
+        }
+        cur = nxt;
+    }
+}
+void orc_merkle_colmajor_h(const u64 *data, size_t cols, int log_L, int cap_height, u64 *digests, int hasher) {
+    size_t L = 1ULL << log_L;
+    #pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < L; r++) {
+        if (hasher) orc_bn254_hash_or_noop_strided(data + r, cols, L, digests + 4 * r);
+        else hash_leaf_colmajor(data, cols, L, r, digests + 4 * r);
+    }
+    orc_merkle_from_digests_h(digests, log_L, cap_height, hasher);
+}
+void orc_merkle_rowmajor_h(const u64 *data, size_t width, int log_L, int cap_height, u64 *digests, int hasher) {
+    size_t L = 1ULL << log_L;
+    #pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < L; r++) {
+        if (hasher) orc_bn254_hash_or_noop_strided(data + r * width, width, 1, digests + 4 * r);
+        else orc_hash_or_noop(data + r * width, width, digests + 4 * r);
+    }
+    orc_merkle_from_digests_h(digests, log_L, cap_height, hasher);
+}
+
 void orc_merkle_from_digests(u64 *digests, int log_L, int cap_height) {
     size_t L = 1ULL << log_L;
     u64 *cur = digests;

@@ -24,6 +24,8 @@ void orc_lde_batch(const u64 *coeffs, size_t cols, int log_n, int rate_bits, u64
 size_t orc_merkle_num_u64(int log_L, int cap_height);
 void orc_merkle_colmajor(const u64 *data, size_t cols, int log_L, int cap_height, u64 *digests);
 void orc_merkle_rowmajor(const u64 *data, size_t width, int log_L, int cap_height, u64 *digests);
+void orc_merkle_colmajor_h(const u64 *data, size_t cols, int log_L, int cap_height, u64 *digests, int hasher);
+void orc_merkle_rowmajor_h(const u64 *data, size_t width, int log_L, int cap_height, u64 *digests, int hasher);
 
 typedef struct {
     uint32_t num_wires, num_routed, num_constants, num_challenges, degree_bits, rate_bits, cap_height, pow_bits,
@@ -32,6 +34,7 @@ typedef struct {
     uint32_t num_gates;
     const orc_gate *gates;
     const u64 *k_is;
+    uint32_t hasher;      /* 0 = PoseidonGoldilocksConfig, 1 = PoseidonBN128GoldilocksConfig */
 } orc_common;
 
 /* ---------------- challenger (challenger.go:42-165) ---------------- */
@@ -48,6 +51,13 @@ static void ch_observe(chal *c, u64 x) { c->nout = 0; c->in[c->nin++] = x; if (c
 static void ch_observe_n(chal *c, const u64 *x, size_t n) { for (size_t i = 0; i < n; i++) ch_observe(c, x[i]); }
 static u64 ch_get(chal *c) { if (c->nin || !c->nout) ch_duplex(c); return c->out[--c->nout]; }
 static e2 ch_get_ext(chal *c) { e2 r; r.a = ch_get(c); r.b = ch_get(c); return r; }
+/* observe a Merkle/sponge hash: GL = its 4 elements; BN128 = the 32 LE bytes in 7-byte chunks (config.rs:58-69) */
+static void ch_observe_hash(chal *c, const u64 h[4], int hasher) {
+    if (!hasher) { ch_observe_n(c, h, 4); return; }
+    uint8_t b[32]; memcpy(b, h, 32);
+    for (int i = 0; i < 32; i += 7) { u64 v = 0; for (int j = 0; j < 7 && i + j < 32; j++) v |= (u64)b[i + j] << (8 * j); ch_observe(c, v); }
+}
+static void ch_observe_cap(chal *c, const u64 *cap, size_t n_hashes, int hasher) { for (size_t i = 0; i < n_hashes; i++) ch_observe_hash(c, cap + 4 * i, hasher); }
 
 /* ---------------- byte writer ---------------- */
 typedef struct { uint8_t *p; size_t len, cap; } wbuf;
@@ -59,24 +69,24 @@ static void wb_u64(wbuf *w, u64 x) { wb_put(w, &x, 8); }
 static void wb_u8(wbuf *w, uint8_t x) { wb_put(w, &x, 1); }
 
 /* ---------------- commitment bundle ---------------- */
-typedef struct { size_t cols; int log_n, rate_bits, cap_height; u64 *coeffs, *lde, *digests; } batch;
+typedef struct { size_t cols; int log_n, rate_bits, cap_height, hasher; u64 *coeffs, *lde, *digests; } batch;
 static const u64 *batch_cap(const batch *b) {
     return b->digests + orc_merkle_num_u64(b->log_n + b->rate_bits, b->cap_height) - (4ULL << b->cap_height);
 }
-static void batch_from_coeffs(batch *b, size_t cols, int log_n, int rate_bits, int cap_height) {
+static void batch_from_coeffs(batch *b, size_t cols, int log_n, int rate_bits, int cap_height, int hasher) {
     size_t n = 1ULL << log_n;
-    b->cols = cols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->hasher = hasher; b->cols = cols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
     b->lde = (u64 *)malloc(cols * (n << rate_bits) * 8);
     b->digests = (u64 *)malloc(orc_merkle_num_u64(log_n + rate_bits, cap_height) * 8);
     orc_lde_batch(b->coeffs, cols, log_n, rate_bits, GL_GEN, b->lde);
-    orc_merkle_colmajor(b->lde, cols, log_n + rate_bits, cap_height, b->digests);
+    orc_merkle_colmajor_h(b->lde, cols, log_n + rate_bits, cap_height, b->digests, hasher);
 }
-static void batch_from_values(batch *b, const u64 *values, size_t cols, int log_n, int rate_bits, int cap_height) {
+static void batch_from_values(batch *b, const u64 *values, size_t cols, int log_n, int rate_bits, int cap_height, int hasher) {
     size_t n = 1ULL << log_n;
     b->coeffs = (u64 *)malloc(cols * n * 8);
     memcpy(b->coeffs, values, cols * n * 8);
     orc_ntt_batch(b->coeffs, cols, log_n, 1);
-    batch_from_coeffs(b, cols, log_n, rate_bits, cap_height);
+    batch_from_coeffs(b, cols, log_n, rate_bits, cap_height, hasher);
 }
 static void batch_free(batch *b) { free(b->coeffs); free(b->lde); free(b->digests); memset(b, 0, sizeof *b); }
 
@@ -87,7 +97,7 @@ orc_circuit *orc_circuit_new(const orc_common *c, const u64 *const_sigma_values,
     orc_circuit *k = (orc_circuit *)calloc(1, sizeof *k);
     k->c = *c;
     size_t n = 1ULL << c->degree_bits;
-    batch_from_values(&k->cs, const_sigma_values, c->num_constants + c->num_routed, (int)c->degree_bits, (int)c->rate_bits, (int)c->cap_height);
+    batch_from_values(&k->cs, const_sigma_values, c->num_constants + c->num_routed, (int)c->degree_bits, (int)c->rate_bits, (int)c->cap_height, (int)c->hasher);
     k->sigma_values = (u64 *)malloc((size_t)c->num_routed * n * 8);
     memcpy(k->sigma_values, const_sigma_values + (size_t)c->num_constants * n, (size_t)c->num_routed * n * 8);
     memcpy(k->digest, digest, 32);
@@ -126,10 +136,11 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
     if (qdf != (1u << rb)) return -5;
 
     u64 pi_hash[4]; orc_hash_no_pad(pis, c->num_pi, pi_hash);
-    batch wires; batch_from_values(&wires, wires_values, W, nlog, rb, ch_h);
+    const int HS = (int)c->hasher; const size_t ncaph = 1ULL << ch_h;
+    batch wires; batch_from_values(&wires, wires_values, W, nlog, rb, ch_h, HS);
 
     chal ch; ch_init(&ch);
-    ch_observe_n(&ch, k->digest, 4); ch_observe_n(&ch, pi_hash, 4); ch_observe_n(&ch, batch_cap(&wires), capn);
+    ch_observe_hash(&ch, k->digest, HS); ch_observe_n(&ch, pi_hash, 4); ch_observe_cap(&ch, batch_cap(&wires), ncaph, HS);
     u64 betas[4], gammas[4], alphas[4];
     for (uint32_t i = 0; i < nch; i++) betas[i] = ch_get(&ch);
     for (uint32_t i = 0; i < nch; i++) gammas[i] = ch_get(&ch);
@@ -171,8 +182,8 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         if (z != 1) { fprintf(stderr, "orc_prove: permutation product != 1 (copy constraints violated)\n"); }
     }
     if (dbg && dbg->zs_pp_values) memcpy(dbg->zs_pp_values, zs_pp, (size_t)nzp * n * 8);
-    batch zsb; batch_from_values(&zsb, zs_pp, nzp, nlog, rb, ch_h);
-    ch_observe_n(&ch, batch_cap(&zsb), capn);
+    batch zsb; batch_from_values(&zsb, zs_pp, nzp, nlog, rb, ch_h, HS);
+    ch_observe_cap(&ch, batch_cap(&zsb), ncaph, HS);
     for (uint32_t i = 0; i < nch; i++) alphas[i] = ch_get(&ch);
 
     /* ---- quotient (prover.rs::compute_quotient_polys) ---- */
@@ -241,8 +252,8 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
     }
     free(qvals);
     if (dbg && dbg->quotient_coeffs) memcpy(dbg->quotient_coeffs, quot.coeffs, (size_t)nch * qdf * n * 8);
-    batch_from_coeffs(&quot, (size_t)nch * qdf, nlog, rb, ch_h);
-    ch_observe_n(&ch, batch_cap(&quot), capn);
+    batch_from_coeffs(&quot, (size_t)nch * qdf, nlog, rb, ch_h, HS);
+    ch_observe_cap(&ch, batch_cap(&quot), ncaph, HS);
     e2 zeta = ch_get_ext(&ch);
 
     /* ---- openings ---- */
@@ -339,11 +350,11 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         if (li == 0 && dbg && dbg->fri_values0) memcpy(dbg->fri_values0, leaves, cur_len * 16);
         int logleaves = cur_log - ab;
         u64 *dg = (u64 *)malloc(orc_merkle_num_u64(logleaves, ch_h) * 8);
-        orc_merkle_rowmajor(leaves, 2 * arity, logleaves, ch_h, dg);
+        orc_merkle_rowmajor_h(leaves, 2 * arity, logleaves, ch_h, dg, HS);
         fri_leaves[li] = leaves; fri_digests[li] = dg; fri_logleaves[li] = logleaves;
         const u64 *cap = dg + orc_merkle_num_u64(logleaves, ch_h) - capn;
         wb_put(&out, cap, capn * 8);
-        ch_observe_n(&ch, cap, capn);
+        ch_observe_cap(&ch, cap, ncaph, HS);
         e2 beta = ch_get_ext(&ch);
         if (dbg) { dbg->fri_betas[li][0] = beta.a; dbg->fri_betas[li][1] = beta.b; }
         /* coeffs = chunks(arity).map(reduce_with_powers(chunk, beta)) */

@@ -11,7 +11,8 @@ class OrcCommon(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in (
         "num_wires", "num_routed", "num_constants", "num_challenges", "degree_bits", "rate_bits", "cap_height", "pow_bits",
         "num_queries", "qdf", "npp", "num_gate_constraints", "num_pi", "num_selectors", "n_arity")] + [
-        ("arity_bits", ctypes.c_uint32 * 16), ("num_gates", ctypes.c_uint32), ("gates", ctypes.c_void_p), ("k_is", ctypes.c_void_p)]
+        ("arity_bits", ctypes.c_uint32 * 16), ("num_gates", ctypes.c_uint32), ("gates", ctypes.c_void_p), ("k_is", ctypes.c_void_p),
+        ("hasher", ctypes.c_uint32)]
 
 class OrcDebug(ctypes.Structure):
     _fields_ = [("betas", ctypes.c_uint64 * 4), ("gammas", ctypes.c_uint64 * 4), ("alphas", ctypes.c_uint64 * 4),
@@ -47,13 +48,14 @@ def common_data(common: dict) -> io.CommonData:
         selector_indices=list(c["selector_indices"]), groups=[tuple(g) for g in c["groups"]],
         quotient_degree_factor=c["quotient_degree_factor"], num_gate_constraints=c["num_gate_constraints"],
         num_constants=c["num_constants"], num_public_inputs=c["num_public_inputs"], k_is=list(c["k_is"]),
-        num_partial_products=c["num_partial_products"], hasher="gl")
+        num_partial_products=c["num_partial_products"], hasher=c.get("hasher", "gl"))
 
 class OracleCircuit:
     """build()'s prover-side half on the CPU: constants/sigmas commitment + digest."""
     def __init__(self, common: dict, constants_sigmas):
         self.lib = cbind.lib()
         self.common = common
+        self.hasher = common.get("hasher", "gl")
         c = common
         self.gate_arr, self._keep = cgates.make_gate_array(c["gates"], c["selector_indices"], c["groups"])
         self.kis = np.array(c["k_is"], dtype=np.uint64)
@@ -65,6 +67,7 @@ class OracleCircuit:
         oc.num_pi = c["num_public_inputs"]; oc.num_selectors = len(c["groups"]); oc.n_arity = len(c["reduction_arity_bits"])
         for i, b in enumerate(c["reduction_arity_bits"]): oc.arity_bits[i] = b
         oc.num_gates = len(c["gates"]); oc.gates = ctypes.addressof(self.gate_arr); oc.k_is = self.kis.ctypes.data
+        oc.hasher = 1 if self.hasher == "bn254" else 0
         self.oc = oc
         cs = np.ascontiguousarray(constants_sigmas, dtype=np.uint64)
         cap = np.zeros((1 << c["cap_height"], 4), dtype=np.uint64)
@@ -73,10 +76,18 @@ class OracleCircuit:
         self.h = ctypes.c_void_p(self.lib.orc_circuit_new(ctypes.byref(oc), cs.ctypes.data_as(ctypes.c_void_p), zero,
                                                           cap.ctypes.data_as(ctypes.c_void_p)))
         self.cap = cap
-        self.digest = circuit_digest_gl(cap, c["degree_bits"])
+        if self.hasher == "bn254":
+            self.cap_ints = [sum(int(h[i]) << (64 * i) for i in range(4)) for h in cap]
+            d = circuit_digest_bn254(self.cap_ints, c["degree_bits"])
+            self.digest_int = d
+            self.digest = [(d >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+        else:
+            self.digest = circuit_digest_gl(cap, c["degree_bits"])
         self.lib.orc_circuit_set_digest(self.h, (ctypes.c_uint64 * 4)(*self.digest))
 
     def verifier_only(self):
+        if self.hasher == "bn254":
+            return io.VerifierOnly(list(self.cap_ints), self.digest_int)
         return io.VerifierOnly([tuple(int(x) for x in h) for h in self.cap], tuple(self.digest))
 
     def prove(self, wires, public_inputs, pow_hint=0, debug=False):

@@ -35,6 +35,26 @@ def test_gpu_proof_bytes_equal_oracle_and_verify(ctx, kind, db):
     assert gpu == cpu, "GPU proof bytes differ from the oracle prover's"
     cd.free()
 
+@pytest.mark.parametrize("db", [6, 9, 12])
+def test_bn128_wrap_config_proof(ctx, db):
+    """PoseidonBN128GoldilocksConfig (the final wrap proof): all Merkle/sponge hashing over BN254 Fr.  The verifier
+    used here is the one that accepts the reference's golden BN128 wrapper proofs."""
+    from b200_plonky2 import workloads
+    from oracle import prover, proof_io as io, verifier
+    cd = workloads.build("rec", db, seed=21, hasher="bn254")
+    oc = prover.OracleCircuit(cd.common, cd.constants_sigmas)
+    cd.upload(ctx)
+    assert np.array_equal(cd.constants_sigmas_cap, oc.cap)
+    assert list(cd.circuit_digest) == list(oc.digest)
+    gpu = cd.prove(ctx)
+    cdo = prover.common_data(cd.common)
+    assert cdo.hasher == "bn254"
+    assert verifier.verify(cdo, oc.verifier_only(), io.proof_from_bytes(gpu, cdo))
+    assert gpu == oc.prove(cd.wires, cd.public_inputs)
+    if db == 12:      # same shape as the golden final proofs: 127 968 - (97 - 4) * 8 bytes
+        assert len(gpu) == 127968 - (97 - len(cd.public_inputs)) * 8
+    cd.free()
+
 def test_same_circuit_many_witnesses(ctx):
     """the reference reuses one ed25519 circuit for all signatures (ed25519.rs:26-40): one upload, many proves."""
     from b200_plonky2 import workloads

@@ -264,7 +264,7 @@ class CircuitData:
                   "proof_of_work_bits", "num_query_rounds", "quotient_degree_factor", "num_partial_products",
                   "num_gate_constraints", "num_public_inputs"):
             setattr(cc, k, c[k])
-        cc.hasher = 0
+        cc.hasher = 1 if c.get("hasher", "gl") == "bn254" else 0
         cc.num_reduction_arity_bits = len(c["reduction_arity_bits"])
         for i, b in enumerate(c["reduction_arity_bits"]): cc.reduction_arity_bits[i] = b
         cc.num_gates = len(c["gates"])
@@ -295,7 +295,11 @@ class CircuitData:
         ctx._chk(lib.b200_circuit_upload(ctx.h, ctypes.byref(cc), self.constants_sigmas.ctypes.data_as(c_void_p), dg0,
                                          cap.ctypes.data_as(c_void_p), ctypes.byref(h)))
         self.constants_sigmas_cap = cap
-        self.circuit_digest = circuit_digest(cap, self.common["degree_bits"])
+        if self.common.get("hasher", "gl") == "bn254":
+            from .poseidon_bn254_py import circuit_digest as digest_bn254
+            self.circuit_digest = digest_bn254(cap, self.common["degree_bits"])
+        else:
+            self.circuit_digest = circuit_digest(cap, self.common["degree_bits"])
         lib.b200_circuit_free(h)
         dg = (ctypes.c_uint64 * 4)(*self.circuit_digest)
         ctx._chk(lib.b200_circuit_upload(ctx.h, ctypes.byref(cc), self.constants_sigmas.ctypes.data_as(c_void_p), dg,

@@ -61,8 +61,10 @@ def rec_circuit(degree_bits, seed=0, num_public_inputs=4):
     cb.fill_coset_interpolation(b, rng, c[10])
     return b, None
 
-def build(kind, degree_bits, seed=0):
+def build(kind, degree_bits, seed=0, hasher="gl"):
+    """kind: "sig" | "rec"; hasher "bn254" = PoseidonBN128GoldilocksConfig (the final wrap proof, prove_block.rs:279-300)."""
     b, _ = (sig_circuit if kind == "sig" else rec_circuit)(degree_bits, seed)
     cd = b.build()
+    cd.common["hasher"] = hasher
     assert cd.common["degree_bits"] == degree_bits, (cd.common["degree_bits"], degree_bits)
     return cd

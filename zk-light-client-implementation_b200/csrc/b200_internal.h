@@ -59,3 +59,8 @@ static inline size_t merkle_num_u64(int log_L, int cap_height) { return 4 * ((si
 void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digests, cudaStream_t st);
 void merkle_leaves_rowmajor(const u64 *data, size_t width, int log_L, u64 *digests, cudaStream_t st);
 void merkle_build(u64 *digests, int log_L, int cap_height, cudaStream_t st);
+// PoseidonBN128Hash variants (merkle_bn254.cu)
+void merkle_leaves_colmajor_bn254(const u64 *data, size_t cols, int log_L, u64 *digests, cudaStream_t st);
+void merkle_leaves_rowmajor_bn254(const u64 *data, size_t width, int log_L, u64 *digests, cudaStream_t st);
+void merkle_build_bn254(u64 *digests, int log_L, int cap_height, cudaStream_t st);
+enum { HASHER_GL = 0, HASHER_BN254 = 1 };

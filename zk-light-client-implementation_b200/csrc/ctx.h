@@ -40,8 +40,8 @@ struct PhaseTimer {     // RAII: records start/stop events for one named phase w
 const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits);
 // PolynomialBatch::from_values on device buffers: values [cols][n] -> coeffs_br [cols][n], lde [cols][n<<rate], digests
 void commit_values(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, int rate_bits, int cap_height,
-                   u64 *d_coeffs_br, u64 *d_lde, u64 *d_digests);
+                   u64 *d_coeffs_br, u64 *d_lde, u64 *d_digests, int hasher = 0);
 // PolynomialBatch::from_coeffs: coeffs_br given
 void commit_coeffs(b200_ctx *ctx, const u64 *d_coeffs_br, size_t cols, int log_n, int rate_bits, int cap_height,
-                   u64 *d_lde, u64 *d_digests);
+                   u64 *d_lde, u64 *d_digests, int hasher = 0);
 void poseidon_permute_batch(u64 *d_states, size_t count, cudaStream_t st);

@@ -15,6 +15,7 @@
 #include "ctx.h"
 #include "plonk.cuh"
 #include "poseidon.cuh"
+#include "bn254.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -82,6 +83,12 @@ struct Challenger {
     void observe(u64 x) { nout = 0; in[nin++] = x; if (nin == 8) duplex(); }
     void observe_n(const u64 *x, size_t n) { for (size_t i = 0; i < n; i++) observe(x[i]); }
     void observe_ext(gl2 e) { observe(e.a); observe(e.b); }
+    // a Merkle/sponge hash of C::Hasher: 4 elements (Poseidon-GL) or 5 x 56-bit limbs (Poseidon-BN128)
+    void observe_hash(const u64 h[4], int hasher) {
+        if (hasher == HASHER_BN254) { u64 v[5]; bn254_to_vec_host(h, v); observe_n(v, 5); }
+        else observe_n(h, 4);
+    }
+    void observe_cap(const u64 *cap, size_t n_hashes, int hasher) { for (size_t i = 0; i < n_hashes; i++) observe_hash(cap + 4 * i, hasher); }
     u64 get() { if (nin || !nout) duplex(); return out[--nout]; }
     gl2 get_ext() { gl2 r; r.a = get(); r.b = get(); return r; }
 };
@@ -90,7 +97,7 @@ struct Challenger {
 struct b200_circuit {
     b200_ctx *ctx;
     u32 num_wires, num_routed, num_constants, num_challenges, degree_bits, rate_bits, cap_height, pow_bits, num_queries,
-        qdf, npp, num_gate_constraints, num_pi, num_selectors;
+        qdf, npp, num_gate_constraints, num_pi, num_selectors, hasher;
     std::vector<u32> arity_bits;
     std::vector<GateDesc> gates;
     std::vector<u64> k_is;
@@ -143,7 +150,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     const size_t n = size_t(1) << nlog, N = n << rb;
     const u32 W = k->num_wires, R = k->num_routed, NC = k->num_constants, nch = k->num_challenges, qdf = k->qdf, npp = k->npp;
     const u32 nzp = nch * (1 + npp), nq = nch * qdf;
-    const size_t capw = size_t(4) << chh;
+    const size_t capw = size_t(4) << chh, ncap = size_t(1) << chh;
+    const int HS = (int)k->hasher;
     const char *dbg = getenv("B200_DEBUG_DUMP");
     if (n_pis != k->num_pi) throw ApiErr{B200_ERR_BAD_ARG, "b200_prove: wrong number of public inputs"};
     ntt_tables_ensure(ctx->tw, Llog, st);
@@ -165,13 +173,13 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     if (wires_on_device) d_wires = wires_in;
     else { PhaseTimer tm(ctx, "h2d_wires"); u64 *t = A.take((size_t)W * n); CUDA_TRY(cudaMemcpyAsync(t, wires_in, (size_t)W * n * 8, cudaMemcpyHostToDevice, st)); d_wires = t; }
     u64 *w_coeffs = A.take((size_t)W * n), *w_lde = A.take((size_t)W * N), *w_dig = A.take(dig_u64);
-    commit_values(ctx, d_wires, W, nlog, rb, chh, w_coeffs, w_lde, w_dig);
+    commit_values(ctx, d_wires, W, nlog, rb, chh, w_coeffs, w_lde, w_dig, HS);
     std::vector<u64> cap_w(capw), cap_z(capw), cap_q(capw);
     CUDA_TRY(cudaMemcpyAsync(cap_w.data(), w_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
 
     Challenger ch;
-    ch.observe_n(k->digest, 4); ch.observe_n(pi_hash, 4); ch.observe_n(cap_w.data(), capw);
+    ch.observe_hash(k->digest, HS); ch.observe_n(pi_hash, 4); ch.observe_cap(cap_w.data(), ncap, HS);
     u64 betas[MAX_CHALLENGES] = {0, 0}, gammas[MAX_CHALLENGES] = {0, 0}, alphas[MAX_CHALLENGES] = {0, 0};
     for (u32 i = 0; i < nch; i++) betas[i] = ch.get();
     for (u32 i = 0; i < nch; i++) gammas[i] = ch.get();
@@ -181,14 +189,14 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     u64 *pp_scratch = A.take((size_t)nch * (npp + 2) * n + 8192), *d_final_prod = A.take(8);
     { PhaseTimer t(ctx, "partial_products");
     launch_partial_products(d_wires, k->sigma_values.u(), k->d_kis.u(), nlog, R, npp, qdf, nch, betas, gammas, ctx->tw.fwd, zs_vals, pp_scratch, d_final_prod, st); }
-    commit_values(ctx, zs_vals, nzp, nlog, rb, chh, zs_coeffs, zs_lde, zs_dig);
+    commit_values(ctx, zs_vals, nzp, nlog, rb, chh, zs_coeffs, zs_lde, zs_dig, HS);
     u64 final_prod[MAX_CHALLENGES];
     CUDA_TRY(cudaMemcpyAsync(cap_z.data(), zs_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(final_prod, d_final_prod, nch * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (u32 i = 0; i < nch; i++) if (final_prod[i] != 1) throw ApiErr{B200_ERR_UNSATISFIED, "permutation argument: grand product != 1 (copy constraints violated)"};
     if (dbg) dump_dev(dbg, "zs_pp_values.bin", zs_vals, (size_t)nzp * n * 8, st);
-    ch.observe_n(cap_z.data(), capw);
+    ch.observe_cap(cap_z.data(), ncap, HS);
     for (u32 i = 0; i < nch; i++) alphas[i] = ch.get();
 
     // ---- quotient ----
@@ -223,11 +231,11 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     }
     u64 *q_coeffs = A.take((size_t)nq * n), *q_lde = A.take((size_t)nq * N), *q_dig = A.take(dig_u64);
     launch_quotient_split(ctx->tmp_q_big, q_coeffs, nlog, rb, nch, st);
-    commit_coeffs(ctx, q_coeffs, nq, nlog, rb, chh, q_lde, q_dig);
+    commit_coeffs(ctx, q_coeffs, nq, nlog, rb, chh, q_lde, q_dig, HS);
     CUDA_TRY(cudaMemcpyAsync(cap_q.data(), q_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (dbg) dump_dev(dbg, "quotient_coeffs_br.bin", q_coeffs, (size_t)nq * n * 8, st);
-    ch.observe_n(cap_q.data(), capw);
+    ch.observe_cap(cap_q.data(), ncap, HS);
     gl2 zeta = ch.get_ext();
     if (gl2_eq(gl2_pow(zeta, (u64)n), gl2_make(1, 0))) throw ApiErr{B200_ERR_UNSATISFIED, "opening point zeta lies in the subgroup"};
 
@@ -287,12 +295,12 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         PhaseTimer tl(ctx, "fri_layers");
         Layer Ly; Ly.vals = cur; Ly.log_len = cur_log; Ly.log_leaves = cur_log - ab; Ly.dig_u64 = merkle_num_u64(Ly.log_leaves, chh);
         Ly.dig = A.take(Ly.dig_u64);
-        merkle_leaves_rowmajor((const u64 *)cur, size_t(2) << ab, Ly.log_leaves, Ly.dig, st);
-        merkle_build(Ly.dig, Ly.log_leaves, chh, st);
+        if (HS == HASHER_BN254) { merkle_leaves_rowmajor_bn254((const u64 *)cur, size_t(2) << ab, Ly.log_leaves, Ly.dig, st); merkle_build_bn254(Ly.dig, Ly.log_leaves, chh, st); }
+        else { merkle_leaves_rowmajor((const u64 *)cur, size_t(2) << ab, Ly.log_leaves, Ly.dig, st); merkle_build(Ly.dig, Ly.log_leaves, chh, st); }
         std::vector<u64> cap(capw);
         CUDA_TRY(cudaMemcpyAsync(cap.data(), Ly.dig + Ly.dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        ch.observe_n(cap.data(), capw);
+        ch.observe_cap(cap.data(), ncap, HS);
         gl2 beta = ch.get_ext();
         fri_betas.push_back(beta); layer_caps.push_back(cap); layers.push_back(Ly);
         gl2 *nxt = pool + fri_pool_used; fri_pool_used += size_t(1) << (cur_log - ab);
@@ -452,7 +460,7 @@ int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_
     API_BEGIN(ctx)
     if (!c || !cs_values || !digest || !out) throw ApiErr{B200_ERR_BAD_ARG, "b200_circuit_upload: null argument"};
     *out = nullptr;
-    if (c->hasher != 0) throw ApiErr{B200_ERR_UNSUPPORTED, "only PoseidonGoldilocksConfig (hasher 0) is implemented; the PoseidonBN128 wrap is a 'next' row"};
+    if (c->hasher > 1) throw ApiErr{B200_ERR_UNSUPPORTED, "hasher must be 0 (PoseidonGoldilocksConfig) or 1 (PoseidonBN128GoldilocksConfig)"};
     if (c->num_challenges == 0 || c->num_challenges > MAX_CHALLENGES) throw ApiErr{B200_ERR_UNSUPPORTED, "num_challenges must be 1 or 2"};
     if (c->quotient_degree_factor != (1u << c->rate_bits)) throw ApiErr{B200_ERR_UNSUPPORTED, "quotient_degree_factor must equal 2^rate_bits"};
     if (c->degree_bits < 2 || c->degree_bits + c->rate_bits > 28) throw ApiErr{B200_ERR_BAD_ARG, "degree_bits out of range"};
@@ -466,7 +474,7 @@ int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_
     k->num_wires = c->num_wires; k->num_routed = c->num_routed_wires; k->num_constants = c->num_constants; k->num_challenges = c->num_challenges;
     k->degree_bits = c->degree_bits; k->rate_bits = c->rate_bits; k->cap_height = c->cap_height; k->pow_bits = c->proof_of_work_bits;
     k->num_queries = c->num_query_rounds; k->qdf = c->quotient_degree_factor; k->npp = c->num_partial_products;
-    k->num_gate_constraints = c->num_gate_constraints; k->num_pi = c->num_public_inputs; k->num_selectors = c->num_selector_groups;
+    k->num_gate_constraints = c->num_gate_constraints; k->num_pi = c->num_public_inputs; k->num_selectors = c->num_selector_groups; k->hasher = c->hasher;
     int bits_left = (int)c->degree_bits + (int)c->rate_bits;
     for (u32 i = 0; i < c->num_reduction_arity_bits; i++) {
         u32 ab = c->reduction_arity_bits[i];
@@ -500,7 +508,7 @@ int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_
     k->cs_coeffs.alloc(cols * n * 8); k->cs_lde.alloc(cols * N * 8);
     size_t nd = merkle_num_u64((int)(c->degree_bits + c->rate_bits), (int)c->cap_height);
     k->cs_digests.alloc(nd * 8);
-    commit_values(ctx, vals.u(), cols, (int)c->degree_bits, (int)c->rate_bits, (int)c->cap_height, k->cs_coeffs.u(), k->cs_lde.u(), k->cs_digests.u());
+    commit_values(ctx, vals.u(), cols, (int)c->degree_bits, (int)c->rate_bits, (int)c->cap_height, k->cs_coeffs.u(), k->cs_lde.u(), k->cs_digests.u(), (int)c->hasher);
     k->sigma_values.alloc((size_t)c->num_routed_wires * n * 8);
     CUDA_TRY(cudaMemcpyAsync(k->sigma_values.p, vals.u() + (size_t)c->num_constants * n, (size_t)c->num_routed_wires * n * 8, cudaMemcpyDeviceToDevice, st));
     if (cap_out) CUDA_TRY(cudaMemcpyAsync(cap_out, k->cs_digests.u() + nd - (size_t(4) << c->cap_height), size_t(32) << c->cap_height, cudaMemcpyDeviceToHost, st));
