@@ -176,7 +176,9 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "k_leaves_colmajor (Poseidon sponge over the 234-column wires LDE, 2^20 leaves)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": None, "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": 2.0067e9 if args.log_n == 17 else None,
+                "traffic_source": "profiles/ncu_k_leaves_colmajor_r01_v3.json: dram read 1.970 GB + write 0.0365 GB per launch (ncu --set full, degree_bits 17)",
+                "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": (leaf[0] / ms_dev) if ms_dev else None,
                 "alu_note": {"permutations_per_launch": perms, "Mperm_per_s": perms / (per_launch_ms * 1e-3) / 1e6 if per_launch_ms else None,
                              "comment": "integer-ALU bound (IMAD.WIDE.U32 issue rate), not HBM bound; see DESIGN.md"}}
@@ -188,6 +190,27 @@ def run_b200(args):
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
                 "phases_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in phases.items()},
                 "proof_bytes": proof_len[0]}
+    if world == 1 and not args.no_aux:
+        # the other proof shapes of one BFT-finality block (second half of BASELINE.json's metric): a recursive_proof-shaped
+        # circuit (13 standard gates, 135 wires, 2^13 rows) and the final PoseidonBN128 wrap (2^12 rows), ms per proof
+        aux = {}
+        for name, kind, db, hs in (("recursive_proof_2^13_ms", "rec", 13, "gl"), ("bn128_wrap_2^12_ms", "rec", 12, "bn254")):
+            try:
+                c2 = workloads.build(kind, db, seed=3, hasher=hs); c2.upload(ctx)
+                c2.prove(ctx); torch.cuda.synchronize()
+                t0 = time.time()
+                for _ in range(3): c2.prove(ctx)
+                torch.cuda.synchronize()
+                aux[name] = round((time.time() - t0) / 3 * 1e3, 3)
+                c2.free()
+            except Exception as e:
+                aux[name] = f"failed: {e}"
+        k = 73
+        if all(isinstance(v, float) for v in aux.values()):
+            aux["bft_block_estimate_ms"] = round(k * ms_e2e / args.steps + (k + 55) * aux["recursive_proof_2^13_ms"] + aux["bn128_wrap_2^12_ms"], 1)
+            aux["bft_block_estimate_note"] = ("k=73 signed approvals (prove_random fixture): k sig-shaped proofs + (k+55) recursive_proof-shaped proofs + 1 BN128 wrap, "
+                                              "prover time only (no witness generation / circuit builds, which stay in Rust); SHA-256 sub-proofs not included")
+        out_json["aux_proof_shapes"] = aux
     if world == 1 and not args.no_cpu_baseline:
         try:
             v, info = cpu_sample(min(args.cpu_sample_log_n, args.log_n), args.log_n, check_ctx=ctx)
@@ -207,6 +230,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=17)
     ap.add_argument("--cpu-sample-log-n", type=int, default=14)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference": run_reference(args)
     else: run_b200(args)

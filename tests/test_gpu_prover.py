@@ -35,7 +35,7 @@ def test_gpu_proof_bytes_equal_oracle_and_verify(ctx, kind, db):
     assert gpu == cpu, "GPU proof bytes differ from the oracle prover's"
     cd.free()
 
-@pytest.mark.parametrize("db", [6, 9, 12])
+@pytest.mark.parametrize("db", [6, 12])
 def test_bn128_wrap_config_proof(ctx, db):
     """PoseidonBN128GoldilocksConfig (the final wrap proof): all Merkle/sponge hashing over BN254 Fr.  The verifier
     used here is the one that accepts the reference's golden BN128 wrapper proofs."""
