@@ -53,7 +53,16 @@ GL_HD fr_t fr_add(const fr_t &a, const fr_t &b) {
     if (c || fr_geq_mod(r.v)) fr_sub_mod(r.v);
     return r;
 }
-GL_HD fr_t fr_mul(const fr_t &a, const fr_t &b) {        // Montgomery CIOS
+// On the device fr_mul is ONE out-of-line function (the first build inlined it ~900 times: 25 k instructions per kernel,
+// instruction-fetch bound); loops over it stay rolled.
+#ifdef __CUDACC__
+#define BN_FN static __host__ __device__ __noinline__
+#define BN_ROLL _Pragma("unroll 1")
+#else
+#define BN_FN static inline
+#define BN_ROLL
+#endif
+BN_FN fr_t fr_mul(const fr_t &a, const fr_t &b) {        // Montgomery CIOS
     const u64 m[4] = {FR_M0, FR_M1, FR_M2, FR_M3};
     u64 t[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
@@ -81,37 +90,48 @@ GL_HD void fr_to_canonical(const fr_t &a, u64 out[4]) {
     fr_t r = fr_mul(a, one);
     for (int i = 0; i < 4; i++) out[i] = r.v[i];
 }
-GL_HD fr_t fr_exp5(const fr_t &x) { fr_t x2 = fr_mul(x, x); return fr_mul(fr_mul(x2, x2), x); }
+BN_FN fr_t fr_exp5(const fr_t &x) { fr_t x2 = fr_mul(x, x); return fr_mul(fr_mul(x2, x2), x); }
 
-GL_HD void bn254_mix(fr_t s[4], const u64 (*m)[4]) {     // result[i] = sum_j m[j][i] * s[j]
+BN_FN void bn254_mix(fr_t s[4], const u64 (*m)[4]) {     // result[i] = sum_j m[j][i] * s[j]
     fr_t r[4];
+    BN_ROLL
     for (int i = 0; i < 4; i++) {
         fr_t acc = fr_mul(fr_load(m, i), s[0]);
+        BN_ROLL
         for (int j = 1; j < 4; j++) acc = fr_add(acc, fr_mul(fr_load(m, 4 * j + i), s[j]));
         r[i] = acc;
     }
     for (int i = 0; i < 4; i++) s[i] = r[i];
 }
 // state in Montgomery form
-GL_HD void bn254_permute(fr_t s[4]) {
+BN_FN void bn254_permute(fr_t s[4]) {
     for (int i = 0; i < 4; i++) s[i] = fr_add(s[i], fr_load(BT(BN254_C), i));
+    BN_ROLL
     for (int r = 0; r < 3; r++) {
+        BN_ROLL
         for (int i = 0; i < 4; i++) s[i] = fr_add(fr_exp5(s[i]), fr_load(BT(BN254_C), (r + 1) * 4 + i));
         bn254_mix(s, BT(BN254_M));
     }
+    BN_ROLL
     for (int i = 0; i < 4; i++) s[i] = fr_add(fr_exp5(s[i]), fr_load(BT(BN254_C), 16 + i));
     bn254_mix(s, BT(BN254_P));
+    BN_ROLL
     for (int r = 0; r < 56; r++) {
         s[0] = fr_add(fr_exp5(s[0]), fr_load(BT(BN254_C), 20 + r));
         fr_t n0 = fr_mul(fr_load(BT(BN254_S), 7 * r), s[0]);
+        BN_ROLL
         for (int j = 1; j < 4; j++) n0 = fr_add(n0, fr_mul(fr_load(BT(BN254_S), 7 * r + j), s[j]));
+        BN_ROLL
         for (int k = 1; k < 4; k++) s[k] = fr_add(s[k], fr_mul(s[0], fr_load(BT(BN254_S), 7 * r + 3 + k)));
         s[0] = n0;
     }
+    BN_ROLL
     for (int r = 0; r < 3; r++) {
+        BN_ROLL
         for (int i = 0; i < 4; i++) s[i] = fr_add(fr_exp5(s[i]), fr_load(BT(BN254_C), 76 + r * 4 + i));
         bn254_mix(s, BT(BN254_M));
     }
+    BN_ROLL
     for (int i = 0; i < 4; i++) s[i] = fr_exp5(s[i]);
     bn254_mix(s, BT(BN254_M));
 }
