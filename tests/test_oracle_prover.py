@@ -44,3 +44,38 @@ def test_pow_hint_semantics():
     b1 = oc.prove(cd.wires, cd.public_inputs, pow_hint=bad_hint)
     p1 = io.proof_from_bytes(b1, cdo)
     assert p1.pow_witness in (p0.pow_witness, bad_hint) and verifier.verify(cdo, oc.verifier_only(), p1)
+
+def test_c_bn254_permutation_kats():
+    """C oracle Poseidon-BN254 vs the reference's 4 permutation vectors (crypto/plonky2_bn128/src/poseidon_bn128.rs:133-180)."""
+    import ctypes, numpy as np
+    from oracle import cbind
+    kats = json.load(open(os.path.join(G, "kats.json")))["poseidon_bn254_permutation"]
+    for v in kats:
+        st = np.zeros(16, dtype=np.uint64)
+        for i, x in enumerate(v["in"]):
+            for k in range(4): st[4 * i + k] = (int(x) >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+        cbind.lib().orc_bn254_permute(st.ctypes.data_as(ctypes.c_void_p))
+        out = [sum(int(st[4 * i + k]) << (64 * k) for k in range(4)) for i in range(4)]
+        assert out == [int(x) for x in v["out"]]
+
+def test_oracle_prover_bn128_config_accepted_by_verifier():
+    """PoseidonBN128GoldilocksConfig: the verifier instance that accepts the reference's golden wrapper proofs must
+    accept the oracle prover's BN128-config proofs (13-gate recursion-shaped circuit)."""
+    from b200_plonky2 import workloads
+    cd = workloads.build("rec", 6, seed=8, hasher="bn254")
+    oc = prover.OracleCircuit(cd.common, cd.constants_sigmas)
+    pb = oc.prove(cd.wires, cd.public_inputs)
+    cdo = prover.common_data(cd.common)
+    assert cdo.hasher == "bn254"
+    pr = io.proof_from_bytes(pb, cdo)
+    assert io.proof_to_bytes(pr, "bn254") == pb
+    assert verifier.verify(cdo, oc.verifier_only(), pr)
+
+def test_product_host_bn254_digest_matches_oracle():
+    from b200_plonky2 import poseidon_bn254_py as pp
+    from oracle import poseidon_bn254 as pbn
+    assert pp.permute([0, 1, 2, 3]) == pbn.permute([0, 1, 2, 3])
+    cap = [[i * 7 + 1, i * 3, 5, 9] for i in range(16)]
+    ints = [sum(h[i] << (64 * i) for i in range(4)) for h in cap]
+    d = prover.circuit_digest_bn254(ints, 12)
+    assert pp.circuit_digest(cap, 12) == [(d >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
