@@ -12,7 +12,7 @@ def test_circuit_digest_formula_matches_golden_wrapper():
     assert prover.circuit_digest_bn254(cap, 12) == int(vd["circuit_digest"])
     assert int(vd["circuit_digest"]) == 15612857049394414280467902980451102556370837276268678037246302844075472795365
 
-@pytest.mark.parametrize("kind,db", [("sig", 8), ("rec", 6), ("rec", 9)])
+@pytest.mark.parametrize("kind,db", [("sig", 8), ("rec", 6), ("rec", 9), ("tiny", 2), ("tiny", 3), ("tiny_pi", 5), ("tiny", 6)])
 def test_oracle_prover_accepted_by_oracle_verifier(kind, db):
     from b200_plonky2 import workloads
     cd = workloads.build(kind, db, seed=5)
@@ -26,7 +26,7 @@ def test_oracle_prover_accepted_by_oracle_verifier(kind, db):
     # minimum-nonce PoW: no smaller witness passes
     assert pr.pow_witness < (1 << 22)
     # a wrong witness must not yield an accepted proof
-    w = cd.wires.copy(); w[3, 5] ^= 1
+    w = cd.wires.copy(); w[0, min(5, cd.n - 1)] ^= 1
     pb2 = oc.prove(w, cd.public_inputs)
     with pytest.raises(verifier.VerifyError):
         verifier.verify(cdo, oc.verifier_only(), io.proof_from_bytes(pb2, cdo))

@@ -61,9 +61,26 @@ def rec_circuit(degree_bits, seed=0, num_public_inputs=4):
     cb.fill_coset_interpolation(b, rng, c[10])
     return b, None
 
+def tiny_circuit(degree_bits, seed=0, num_public_inputs=0):
+    """edge-case circuit: 2^degree_bits rows (>= 4) of arithmetic / constant gates, optional public inputs; small enough
+    that FRI has no reduction layer (degree_bits <= 5)."""
+    cfg = cb.CircuitConfig.standard_recursion_config()
+    rng = np.random.default_rng(seed)
+    b = cb.CircuitBuilder(cfg)
+    if num_public_inputs:
+        b.register_public_inputs([int(x) for x in rng.integers(0, 1 << 32, size=num_public_inputs)])
+    budget = (1 << degree_bits) - b.num_rows
+    a = max(1, budget // 2)
+    cb.fill_arithmetic(b, rng, a)
+    if budget - a > 0:
+        cb.fill_constant(b, rng.integers(0, 1 << 62, size=(budget - a, 2), dtype=np.uint64))
+    return b, None
+
 def build(kind, degree_bits, seed=0, hasher="gl"):
     """kind: "sig" | "rec"; hasher "bn254" = PoseidonBN128GoldilocksConfig (the final wrap proof, prove_block.rs:279-300)."""
-    b, _ = (sig_circuit if kind == "sig" else rec_circuit)(degree_bits, seed)
+    if kind == "tiny": b, _ = tiny_circuit(degree_bits, seed)
+    elif kind == "tiny_pi": b, _ = tiny_circuit(degree_bits, seed, 3)
+    else: b, _ = (sig_circuit if kind == "sig" else rec_circuit)(degree_bits, seed)
     cd = b.build()
     cd.common["hasher"] = hasher
     assert cd.common["degree_bits"] == degree_bits, (cd.common["degree_bits"], degree_bits)
