@@ -492,22 +492,32 @@ def fill_poseidon(b, inputs, swap):
     rows = b.add_rows(poseidon_gate(), np.zeros((cnt, 0), np.uint64), w)
     return rows, out
 
-def fill_poseidon_chain(b, rng, cnt):
-    """cnt rows, row r+1 input[4..8) = row r output[0..4) (Merkle-path-like chain) -- cross-row copy constraints."""
-    inp = F.canon(rng.integers(0, 1 << 63, size=(1, 12), dtype=np.uint64))
-    all_in = np.zeros((cnt, 12), np.uint64); sw = rng.integers(0, 2, size=cnt, dtype=np.uint64)
-    cur = inp[0]
-    for r in range(cnt):
-        all_in[r] = cur
+def fill_poseidon_chain(b, rng, cnt, chain_len=16):
+    """cnt rows organised as Merkle-path-like chains of `chain_len` rows: row r+1 input[4..8) = row r output[0..4)
+    (cross-row copy constraints).  Chains are independent, so every step is vectorised over all chains."""
+    chain_len = max(1, min(chain_len, cnt))
+    nchains = -(-cnt // chain_len)
+    total = nchains * chain_len
+    all_in = np.zeros((chain_len, nchains, 12), np.uint64)
+    sw = rng.integers(0, 2, size=(chain_len, nchains), dtype=np.uint64)
+    cur = F.canon(rng.integers(0, 1 << 63, size=(nchains, 12), dtype=np.uint64))
+    for step in range(chain_len):
+        all_in[step] = cur
         st = cur.copy()
-        if sw[r]:
-            st[0:4], st[4:8] = cur[4:8].copy(), cur[0:4].copy()
-        out = poseidon_np.permute_trace(st[None, :])[0][0]
-        nxt = F.canon(rng.integers(0, 1 << 63, size=12, dtype=np.uint64)); nxt[4:8] = out[0:4]
+        m = sw[step].astype(bool)
+        st[m, 0:4], st[m, 4:8] = cur[m, 4:8], cur[m, 0:4]
+        out = poseidon_np.permute(st)
+        nxt = F.canon(rng.integers(0, 1 << 63, size=(nchains, 12), dtype=np.uint64)); nxt[:, 4:8] = out[:, 0:4]
         cur = nxt
-    rows, _ = fill_poseidon(b, all_in, sw)
+    # row order: chain-major (rows of one chain are consecutive); drop the surplus rows of the last chain
+    inp = all_in.transpose(1, 0, 2).reshape(total, 12)[:cnt]
+    swf = sw.transpose(1, 0).reshape(total)[:cnt]
+    rows, _ = fill_poseidon(b, inp, swf)
+    idx = np.arange(cnt)
+    link = idx[(idx % chain_len) != chain_len - 1]
+    link = link[link + 1 < cnt]
     for j in range(4):
-        b.connect(rows[:-1], 12 + j, rows[1:], 4 + j)
+        b.connect(rows[link], 12 + j, rows[link + 1], 4 + j)
     return rows
 
 # ---------------------------------------------------------------------------------------------------------------
