@@ -92,15 +92,68 @@ GL_HD void poseidon_mds_half(const i64 x[12], i64 y[12]) {
     }
 }
 
-GL_HD void poseidon_mds(u64 s[12]) {
-    i64 lo[12], hi[12], yl[12], yh[12];
+// Same transform on 32-bit signed integers (inputs < 2^22: |intermediates| < 2^31), used on three 22-bit limbs so that
+// every add is ONE instruction (the 64-bit version needs an add + add-with-carry pair per operation).
+typedef int i32;
+GL_HD void poseidon_mds_limb(const i32 x[12], i32 y[12]) {
+    i32 U0[3], U2[3], Ur[3], Ui[3];
 #pragma unroll
+    for (int r = 0; r < 3; r++) {
+        i32 t0 = x[r] + x[r + 6], t1 = x[r] - x[r + 6], t2 = x[r + 3] + x[r + 9], t3 = x[r + 3] - x[r + 9];
+        U0[r] = t0 + t2; U2[r] = t0 - t2; Ur[r] = t1; Ui[r] = -t3;
+    }
+    const i32 S = U0[0] + U0[1] + U0[2];
+    i32 b0[3] = {(S + U0[2]) << 4, (S + U0[0]) << 4, (S + U0[1]) << 4};
+    i32 b2[3] = {(U2[2] << 3) - U2[0] - (U2[1] << 1), -U2[1] - (U2[0] << 3) - (U2[2] << 1), (U2[0] << 1) - U2[2] - (U2[1] << 3)};
+#define K0RE(b) ((Ur[b] << 1) + Ui[b])
+#define K0IM(b) ((Ui[b] << 1) - Ur[b])
+#define K1RE(b) (-(Ur[b] << 2) - Ui[b])
+#define K1IM(b) (Ur[b] - (Ui[b] << 2))
+#define K2RE(b) ((Ur[b] << 4) - Ui[b])
+#define K2IM(b) ((Ui[b] << 4) + Ur[b])
+    i32 Wre[3], Wim[3];
+    { i32 ar = K1RE(2) + K2RE(1), ai = K1IM(2) + K2IM(1); Wre[0] = K0RE(0) + ai; Wim[0] = K0IM(0) - ar; }
+    { i32 ar = K2RE(2), ai = K2IM(2); Wre[1] = K0RE(1) + K1RE(0) + ai; Wim[1] = K0IM(1) + K1IM(0) - ar; }
+    Wre[2] = K0RE(2) + K1RE(1) + K2RE(0); Wim[2] = K0IM(2) + K1IM(1) + K2IM(0);
+#undef K0RE
+#undef K0IM
+#undef K1RE
+#undef K1IM
+#undef K2RE
+#undef K2IM
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        i32 s = b0[t] + b2[t], d = b0[t] - b2[t];
+        y[t] = s + Wre[t]; y[t + 6] = s - Wre[t]; y[t + 3] = d - Wim[t]; y[t + 9] = d + Wim[t];
+    }
+}
+
+// v = y0 + y1*2^22 + y2*2^44 (0 <= y_k < 2^31) reduced to [0, 2^64)
+GL_HD u64 poseidon_recombine3(u32 y0, u32 y1, u32 y2) {
+    u64 lo = (u64)y0 + ((u64)y1 << 22);            // < 2^54
+    u64 t = (u64)y2 << 12;                         // y2 * 2^44 = t * 2^32,  t < 2^43
+    return poseidon_reduce96(lo, t);
+}
+
+GL_HD void poseidon_mds(u64 s[12]) {
+#ifdef __CUDA_ARCH__
+    i32 l0[12], l1[12], l2[12], y0[12], y1[12], y2[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        l0[i] = (i32)((u32)s[i] & 0x3FFFFFu); l1[i] = (i32)((u32)(s[i] >> 22) & 0x3FFFFFu); l2[i] = (i32)(u32)(s[i] >> 44);
+    }
+    poseidon_mds_limb(l0, y0); poseidon_mds_limb(l1, y1); poseidon_mds_limb(l2, y2);
+    y0[0] += l0[0] << 3; y1[0] += l1[0] << 3; y2[0] += l2[0] << 3;          // diagonal term 8*s[0]
+#pragma unroll
+    for (int r = 0; r < 12; r++) s[r] = poseidon_recombine3((u32)y0[r], (u32)y1[r], (u32)y2[r]);
+#else
+    i64 lo[12], hi[12], yl[12], yh[12];
     for (int i = 0; i < 12; i++) { lo[i] = (i64)(u32)s[i]; hi[i] = (i64)(s[i] >> 32); }
     poseidon_mds_half(lo, yl);
     poseidon_mds_half(hi, yh);
     yl[0] += lo[0] << 3; yh[0] += hi[0] << 3;          // diagonal term 8*s[0]
-#pragma unroll
     for (int r = 0; r < 12; r++) s[r] = poseidon_reduce96((u64)yl[r], (u64)yh[r]);
+#endif
 }
 
 GL_HD void poseidon_full_rounds(u64 s[12], int rc_off) {
