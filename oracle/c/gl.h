@@ -14,8 +14,16 @@ typedef unsigned __int128 u128;
 static inline u64 gl_add(u64 a, u64 b) { u128 s = (u128)a + b; if (s >= GL_P) s -= GL_P; return (u64)s; }
 static inline u64 gl_sub(u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); }
 static inline u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
-static inline u64 gl_mul(u64 a, u64 b) { return (u64)(((u128)a * b) % GL_P); }
-static inline u64 gl_red128(u128 x) { return (u64)(x % GL_P); }
+/* (hi*2^64 + lo) mod p via 2^64 = 2^32 - 1, 2^96 = -1 (the reduction upstream plonky2 uses on the CPU) */
+static inline u64 gl_red128(u128 x) {
+    u64 lo = (u64)x, hi = (u64)(x >> 64);
+    u64 hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
+    u64 t0 = lo - hh; if (lo < hh) t0 -= 0xFFFFFFFFULL;
+    u64 t1 = hl * 0xFFFFFFFFULL;
+    u64 r = t0 + t1; if (r < t1) r += 0xFFFFFFFFULL;
+    return r >= GL_P ? r - GL_P : r;
+}
+static inline u64 gl_mul(u64 a, u64 b) { return gl_red128((u128)a * b); }
 static inline u64 gl_pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = gl_mul(r, a); a = gl_mul(a, a); e >>= 1; } return r; }
 static inline u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
 static inline u64 gl_root(int n_log) { u64 r = GL_ROOT32; for (int i = n_log; i < 32; i++) r = gl_mul(r, r); return r; }

@@ -39,3 +39,14 @@ def test_no_cpu_fallback_without_device(so):
     import b200_plonky2
     with pytest.raises(b200_plonky2.B200Error):
         b200_plonky2.Context(0)
+
+def test_cpp_host_mirror_compiles_links_and_fails_loudly(so, tmp_path):
+    """include/b200_plonky2.hpp (C++ mirror of CircuitData::prove) builds against the .so; without a device the
+    Context constructor throws B200_ERR_CUDA (no CPU fallback), with a device a bad circuit is rejected cleanly."""
+    import subprocess
+    exe = str(tmp_path / "cpp_mirror_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_mirror_check.cpp"),
+                           "-o", exe, "-L", os.path.dirname(SO), "-lb200plonky2", "-Wl,-rpath," + os.path.dirname(SO)])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ("no device" in r.stdout) or ("rejected as expected" in r.stdout)
