@@ -43,6 +43,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     ntt_tables_free(ctx->tw);
     for (auto &kv : ctx->lde_scale) cudaFree(kv.second);
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

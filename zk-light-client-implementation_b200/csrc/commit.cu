@@ -14,6 +14,24 @@ const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits) {
     return p;
 }
 
+void commit_hash_only(b200_ctx *ctx, const u64 *d_lde, size_t cols, int log_n, int rate_bits, int cap_height, u64 *d_digests, int hasher) {
+    if (hasher == HASHER_BN254) {
+        { PhaseTimer t(ctx, cols >= 64 ? "leaf_hash_wide" : "leaf_hash"); merkle_leaves_colmajor_bn254(d_lde, cols, log_n + rate_bits, d_digests, ctx->stream); }
+        { PhaseTimer t(ctx, "merkle_levels"); merkle_build_bn254(d_digests, log_n + rate_bits, cap_height, ctx->stream); }
+        return;
+    }
+    { PhaseTimer t(ctx, cols >= 64 ? "leaf_hash_wide" : "leaf_hash"); merkle_leaves_colmajor(d_lde, cols, log_n + rate_bits, d_digests, ctx->stream); }
+    { PhaseTimer t(ctx, "merkle_levels"); merkle_build(d_digests, log_n + rate_bits, cap_height, ctx->stream); }
+}
+
+void commit_values_lde_only(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, int rate_bits, u64 *d_coeffs_br, u64 *d_lde) {
+    ntt_tables_ensure(ctx->tw, log_n + rate_bits, ctx->stream);
+    const u64 *scale = ctx_lde_scale(ctx, log_n, rate_bits);
+    size_t n = size_t(1) << log_n;
+    { PhaseTimer t(ctx, "intt"); ntt_dif(ctx->tw, d_values, n, false, d_coeffs_br, n, log_n, cols, 0, nullptr, true, gl_inv((u64)n % GL_P), ctx->stream); }
+    { PhaseTimer t(ctx, "lde"); ntt_dif(ctx->tw, d_coeffs_br, n, true, d_lde, n << rate_bits, log_n, cols << rate_bits, rate_bits, scale, false, 1, ctx->stream); }
+}
+
 void commit_coeffs(b200_ctx *ctx, const u64 *d_coeffs_br, size_t cols, int log_n, int rate_bits, int cap_height,
                    u64 *d_lde, u64 *d_digests, int hasher) {
     ntt_tables_ensure(ctx->tw, log_n + rate_bits, ctx->stream);

@@ -19,6 +19,7 @@ struct b200_ctx {
     std::string err;
     void *arena = nullptr; size_t arena_bytes = 0;   // grow-only scratch for b200_prove
     u64 *tmp_q_big = nullptr;
+    cudaStream_t copy_stream = nullptr;               // H2D of host witnesses, overlapped with the LDE
     // optional phase timing (b200_ctx_enable_timing): CUDA events on the context stream around prover phases
     bool timing = false;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timing_events;
@@ -44,4 +45,7 @@ void commit_values(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, i
 // PolynomialBatch::from_coeffs: coeffs_br given
 void commit_coeffs(b200_ctx *ctx, const u64 *d_coeffs_br, size_t cols, int log_n, int rate_bits, int cap_height,
                    u64 *d_lde, u64 *d_digests, int hasher = 0);
+// the two halves of commit_values, for pipelining the host->device copy of the witness with the LDE
+void commit_values_lde_only(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, int rate_bits, u64 *d_coeffs_br, u64 *d_lde);
+void commit_hash_only(b200_ctx *ctx, const u64 *d_lde, size_t cols, int log_n, int rate_bits, int cap_height, u64 *d_digests, int hasher);
 void poseidon_permute_batch(u64 *d_states, size_t count, cudaStream_t st);

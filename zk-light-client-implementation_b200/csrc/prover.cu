@@ -171,9 +171,32 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     u64 pi_hash[4]; poseidon_hash_no_pad_host(pis, n_pis, pi_hash);
     const u64 *d_wires;
     if (wires_on_device) d_wires = wires_in;
-    else { PhaseTimer tm(ctx, "h2d_wires"); u64 *t = A.take((size_t)W * n); CUDA_TRY(cudaMemcpyAsync(t, wires_in, (size_t)W * n * 8, cudaMemcpyHostToDevice, st)); d_wires = t; }
     u64 *w_coeffs = A.take((size_t)W * n), *w_lde = A.take((size_t)W * N), *w_dig = A.take(dig_u64);
-    commit_values(ctx, d_wires, W, nlog, rb, chh, w_coeffs, w_lde, w_dig, HS);
+    if (wires_on_device) commit_values(ctx, d_wires = wires_in, W, nlog, rb, chh, w_coeffs, w_lde, w_dig, HS);
+    else {
+        // host witness: stream it in column chunks on a copy stream and run iNTT + LDE of chunk c while chunk c+1 is in
+        // flight (the LDE takes longer than the PCIe copy, so the H2D time disappears behind it); hash once all columns are in
+        u64 *t = A.take((size_t)W * n); d_wires = t;
+        if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        const u32 nchunks = W >= 32 ? 6 : 1;
+        std::vector<cudaEvent_t> evs(nchunks);
+        cudaEvent_t start_ev; CUDA_TRY(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(start_ev, st)); CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, start_ev, 0));   // arena reuse ordering
+        for (u32 c = 0; c < nchunks; c++) {
+            size_t c0 = (size_t)W * c / nchunks, c1 = (size_t)W * (c + 1) / nchunks;
+            CUDA_TRY(cudaMemcpyAsync(t + c0 * n, wires_in + c0 * n, (c1 - c0) * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CUDA_TRY(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(evs[c], ctx->copy_stream));
+        }
+        for (u32 c = 0; c < nchunks; c++) {
+            size_t c0 = (size_t)W * c / nchunks, c1 = (size_t)W * (c + 1) / nchunks;
+            CUDA_TRY(cudaStreamWaitEvent(st, evs[c], 0));
+            commit_values_lde_only(ctx, t + c0 * n, c1 - c0, nlog, rb, w_coeffs + c0 * n, w_lde + c0 * N);
+        }
+        commit_hash_only(ctx, w_lde, W, nlog, rb, chh, w_dig, HS);
+        for (auto e : evs) cudaEventDestroy(e);
+        cudaEventDestroy(start_ev);
+    }
     std::vector<u64> cap_w(capw), cap_z(capw), cap_q(capw);
     CUDA_TRY(cudaMemcpyAsync(cap_w.data(), w_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
