@@ -37,7 +37,8 @@ typedef enum {
     B200_ERR_CUDA = -2,
     B200_ERR_UNSATISFIED = -3,   /* witness does not satisfy the circuit (quotient not a polynomial) */
     B200_ERR_OOM = -4,
-    B200_ERR_UNSUPPORTED = -5    /* e.g. unknown gate id, zero-knowledge blinding, lookups */
+    B200_ERR_UNSUPPORTED = -5,   /* e.g. unknown gate id, zero-knowledge blinding, lookups */
+    B200_ERR_INVALID_PROOF = -6  /* b200_verify: the proof does not verify */
 } b200_status;
 
 typedef struct b200_ctx b200_ctx;
@@ -106,6 +107,16 @@ int b200_prove(b200_ctx *ctx, const b200_circuit *circuit, const uint64_t *wires
 /* Same, wires already resident in device memory (device pointer). */
 int b200_prove_dev(b200_ctx *ctx, const b200_circuit *circuit, const uint64_t *d_wires, const uint64_t *public_inputs,
                    size_t n_public_inputs, uint64_t pow_witness_hint, uint8_t **proof_bytes, size_t *proof_len);
+
+/* ---- verify (host only, no device needed) ----
+ * CircuitData::verify(proof) (near_bft_finality/src/prove_block_data/header_bphash.rs:94, primitives.rs:110,160).
+ * Returns 0 if the proof verifies, B200_ERR_INVALID_PROOF otherwise (reason from b200_verify_error(), thread-local). */
+typedef struct {
+    const uint64_t *constants_sigmas_cap;   /* 2^cap_height hashes, 4 u64 each (32 LE bytes per hash for hasher 1) */
+    uint64_t circuit_digest[4];
+} b200_verifier_only;
+int b200_verify(const b200_common *common, const b200_verifier_only *verifier_only, const uint8_t *proof, size_t len);
+const char *b200_verify_error(void);
 
 /* ---- inner loops (host-buffer entry points; *_dev variants take device pointers and run asynchronously on
  * the context stream) ---- */

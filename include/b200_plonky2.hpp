@@ -71,6 +71,13 @@ public:
         b200_free(p);
         return out;
     }
+    // CircuitData::verify(proof) (header_bphash.rs:94, primitives.rs:110,160): host-only check, throws on an invalid proof
+    void verify(const ProofWithPublicInputs &proof, const uint64_t circuit_digest[4]) const {
+        b200_verifier_only vo; vo.constants_sigmas_cap = cap_.data();
+        for (int i = 0; i < 4; i++) vo.circuit_digest[i] = circuit_digest[i];
+        int rc = b200_verify(&common_.c, &vo, proof.bytes.data(), proof.bytes.size());
+        if (rc) throw Error(rc, b200_verify_error());
+    }
 private:
     Context &ctx_; CommonCircuitData common_; b200_circuit *circuit_ = nullptr; std::vector<uint64_t> cap_;
 };

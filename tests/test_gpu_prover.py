@@ -32,6 +32,7 @@ def test_gpu_proof_bytes_equal_oracle_and_verify(ctx, kind, db):
     cdo = prover.common_data(cd.common)
     pr = io.proof_from_bytes(gpu, cdo)
     assert verifier.verify(cdo, oc.verifier_only(), pr)
+    assert cd.verify(gpu)                      # the product's own verifier (b200_verify) agrees
     assert gpu == cpu, "GPU proof bytes differ from the oracle prover's"
     cd.free()
 
@@ -51,6 +52,7 @@ def test_bn128_wrap_config_proof(ctx, db):
     assert cdo.hasher == "bn254"
     assert verifier.verify(cdo, oc.verifier_only(), io.proof_from_bytes(gpu, cdo))
     assert gpu == oc.prove(cd.wires, cd.public_inputs)
+    assert cd.verify(gpu)
     if db == 12:      # same shape as the golden final proofs: 127 968 - (97 - 4) * 8 bytes
         assert len(gpu) == 127968 - (97 - len(cd.public_inputs)) * 8
     cd.free()

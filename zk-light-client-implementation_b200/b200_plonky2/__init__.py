@@ -35,6 +35,9 @@ class Common(ctypes.Structure):
         ("num_selector_groups", c_u32), ("group_starts", ctypes.POINTER(c_u32)), ("group_ends", ctypes.POINTER(c_u32)),
         ("k_is", u64p)]
 
+class VerifierOnly(ctypes.Structure):
+    _fields_ = [("constants_sigmas_cap", u64p), ("circuit_digest", c_u64 * 4)]
+
 def _sig(name, restype, *argtypes):
     f = getattr(lib, name); f.restype = restype; f.argtypes = list(argtypes); return f
 
@@ -55,12 +58,14 @@ _sig("b200_lde_commit_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c
 _sig("b200_poseidon_merkle", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p, c_void_p)
 _sig("b200_poseidon_merkle_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p)
 _sig("b200_poseidon_permute", c_int, c_void_p, c_void_p, c_size_t)
+_sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
+_sig("b200_verify_error", ctypes.c_char_p)
 
 EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_synchronize", "b200_last_error",
            "b200_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
            "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
            "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
-           "b200_poseidon_permute"]
+           "b200_poseidon_permute", "b200_verify", "b200_verify_error"]
 
 def _np(a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
@@ -124,3 +129,49 @@ class Context:
         a, p = _np(np.array(states, dtype=np.uint64, copy=True))
         self._chk(lib.b200_poseidon_permute(self.h, p, a.shape[0]))
         return a
+
+
+def common_struct(common: dict):
+    """dict with the common_data.json fields (+ "hasher": "gl" | "bn254") -> (b200_common, keep-alive objects)."""
+    c = common
+    cc = Common()
+    for k in ("num_wires", "num_routed_wires", "num_constants", "num_challenges", "degree_bits", "rate_bits", "cap_height",
+              "proof_of_work_bits", "num_query_rounds", "quotient_degree_factor", "num_partial_products",
+              "num_gate_constraints", "num_public_inputs"):
+        setattr(cc, k, c[k])
+    cc.hasher = 1 if c.get("hasher", "gl") == "bn254" else 0
+    cc.num_reduction_arity_bits = len(c["reduction_arity_bits"])
+    for i, b in enumerate(c["reduction_arity_bits"]): cc.reduction_arity_bits[i] = b
+    cc.num_gates = len(c["gates"])
+    keep = dict(ids=(ctypes.c_char_p * len(c["gates"]))(*[g.encode() for g in c["gates"]]),
+                sel=(c_u32 * len(c["gates"]))(*c["selector_indices"]),
+                gs=(c_u32 * len(c["groups"]))(*[s for s, e in c["groups"]]), ge=(c_u32 * len(c["groups"]))(*[e for s, e in c["groups"]]),
+                kis=np.array(c["k_is"], dtype=np.uint64))
+    cc.gate_ids = ctypes.cast(keep["ids"], ctypes.POINTER(ctypes.c_char_p))
+    cc.selector_indices = ctypes.cast(keep["sel"], ctypes.POINTER(c_u32))
+    cc.num_selector_groups = len(c["groups"])
+    cc.group_starts = ctypes.cast(keep["gs"], ctypes.POINTER(c_u32)); cc.group_ends = ctypes.cast(keep["ge"], ctypes.POINTER(c_u32))
+    cc.k_is = keep["kis"].ctypes.data_as(u64p)
+    return cc, keep
+
+def common_from_json(d: dict, hasher="gl"):
+    """plonky2 common_data.json (as written by near_bft_finality/src/bin/prove_block.rs:343-356) -> the dict used here."""
+    cfg, fp = d["config"], d["fri_params"]
+    return dict(num_wires=cfg["num_wires"], num_routed_wires=cfg["num_routed_wires"], num_constants=d["num_constants"],
+                num_challenges=cfg["num_challenges"], degree_bits=fp["degree_bits"], rate_bits=fp["config"]["rate_bits"],
+                cap_height=fp["config"]["cap_height"], proof_of_work_bits=fp["config"]["proof_of_work_bits"],
+                num_query_rounds=fp["config"]["num_query_rounds"], quotient_degree_factor=d["quotient_degree_factor"],
+                num_partial_products=d["num_partial_products"], num_gate_constraints=d["num_gate_constraints"],
+                num_public_inputs=d["num_public_inputs"], reduction_arity_bits=list(fp["reduction_arity_bits"]),
+                gates=list(d["gates"]), selector_indices=list(d["selectors_info"]["selector_indices"]),
+                groups=[(g["start"], g["end"]) for g in d["selectors_info"]["groups"]], k_is=list(d["k_is"]), hasher=hasher)
+
+def verify(common: dict, constants_sigmas_cap, circuit_digest, proof_bytes: bytes):
+    """CircuitData::verify: constants_sigmas_cap [2^cap_height][4] u64 words, circuit_digest 4 words.  Returns (ok, reason)."""
+    cc, keep = common_struct(common)
+    cap = np.ascontiguousarray(constants_sigmas_cap, dtype=np.uint64)
+    vo = VerifierOnly(); vo.constants_sigmas_cap = cap.ctypes.data_as(u64p)
+    for i in range(4): vo.circuit_digest[i] = int(circuit_digest[i])
+    buf = (ctypes.c_uint8 * len(proof_bytes)).from_buffer_copy(proof_bytes)
+    rc = lib.b200_verify(ctypes.byref(cc), ctypes.byref(vo), buf, len(proof_bytes))
+    return rc == 0, lib.b200_verify_error().decode()

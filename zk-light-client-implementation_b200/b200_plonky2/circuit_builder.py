@@ -320,6 +320,14 @@ class CircuitData:
         lib.b200_free(out)
         return b
 
+    def verify(self, proof_bytes):
+        """CircuitData::verify(proof): host-side check by the product verifier (b200_verify).  Raises on an invalid proof."""
+        from . import verify, B200Error
+        assert self.constants_sigmas_cap is not None, "upload() first (the cap and digest come from the build-side commitment)"
+        ok, why = verify(self.common, self.constants_sigmas_cap, self.circuit_digest, proof_bytes)
+        if not ok: raise B200Error(-6, why)
+        return True
+
     def free(self):
         from . import lib
         if self._handle is not None:

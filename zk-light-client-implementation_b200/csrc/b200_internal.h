@@ -13,6 +13,7 @@
 #define B200_ERR_UNSATISFIED (-3)
 #define B200_ERR_OOM (-4)
 #define B200_ERR_UNSUPPORTED (-5)
+#define B200_ERR_INVALID_PROOF (-6)
 
 struct CudaErr { cudaError_t e; const char *file; int line; };
 #define CUDA_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) throw CudaErr{_e, __FILE__, __LINE__}; } while (0)

@@ -21,77 +21,7 @@
 #include <string.h>
 #include <algorithm>
 
-// ------------------------------------------------------------------------------------------------
-// gate id parsing (plonky2 Gate::id() strings as they appear in common_data.json)
-// ------------------------------------------------------------------------------------------------
-static bool starts_with(const char *s, const char *p) { return strncmp(s, p, strlen(p)) == 0; }
-
-static bool parse_gate(const char *id, GateDesc &g, std::vector<u64> &extra) {
-    memset(&g, 0, sizeof g);
-    unsigned a = 0, b = 0, c = 0;
-    if (strcmp(id, "NoopGate") == 0) { g.kind = G_NOOP; g.num_constraints = 0; return true; }
-    if (sscanf(id, "ConstantGate { num_consts: %u }", &a) == 1) { g.kind = G_CONSTANT; g.p[0] = a; g.num_constraints = a; return true; }
-    if (strcmp(id, "PublicInputGate") == 0) { g.kind = G_PUBLIC_INPUT; g.num_constraints = 4; return true; }
-    if (sscanf(id, "ArithmeticGate { num_ops: %u }", &a) == 1) { g.kind = G_ARITHMETIC; g.p[0] = a; g.num_constraints = a; return true; }
-    if (sscanf(id, "ArithmeticExtensionGate { num_ops: %u }", &a) == 1) { g.kind = G_ARITHMETIC_EXT; g.p[0] = a; g.num_constraints = 2 * a; return true; }
-    if (sscanf(id, "MulExtensionGate { num_ops: %u }", &a) == 1) { g.kind = G_MUL_EXT; g.p[0] = a; g.num_constraints = 2 * a; return true; }
-    if (sscanf(id, "BaseSumGate { num_limbs: %u } + Base: %u", &a, &b) == 2) { g.kind = G_BASE_SUM; g.p[0] = a; g.p[1] = b; g.num_constraints = 1 + a; return true; }
-    if (sscanf(id, "ReducingGate { num_coeffs: %u }", &a) == 1) { g.kind = G_REDUCING; g.p[0] = a; g.num_constraints = 2 * a; return true; }
-    if (sscanf(id, "ReducingExtensionGate { num_coeffs: %u }", &a) == 1) { g.kind = G_REDUCING_EXT; g.p[0] = a; g.num_constraints = 2 * a; return true; }
-    if (sscanf(id, "RandomAccessGate { bits: %u, num_copies: %u, num_extra_constants: %u", &a, &b, &c) == 3) {
-        if (a > 6) return false;
-        g.kind = G_RANDOM_ACCESS; g.p[0] = a; g.p[1] = b; g.p[2] = c; g.num_constraints = b * (a + 2) + c; return true; }
-    if (starts_with(id, "PoseidonMdsGate")) { g.kind = G_POSEIDON_MDS; g.num_constraints = 24; return true; }
-    if (starts_with(id, "PoseidonGate")) { g.kind = G_POSEIDON; g.num_constraints = 123; return true; }
-    if (sscanf(id, "CosetInterpolationGate { subgroup_bits: %u, degree: %u, barycentric_weights: [", &a, &b) == 2) {
-        const char *p = strchr(id, '['); if (!p) return false; p++;
-        g.kind = G_COSET_INTERPOLATION; g.p[0] = a; g.p[1] = b; g.extra_off = (u32)extra.size();
-        unsigned np = 1u << a;
-        for (unsigned i = 0; i < np; i++) {
-            char *end; unsigned long long v = strtoull(p, &end, 10); if (end == p) return false;
-            extra.push_back((u64)v); p = end; while (*p == ',' || *p == ' ') p++;
-        }
-        if (b < 2 || a > 6) return false;
-        unsigned n_inter = (np - 2) / (b - 1);
-        g.num_constraints = 2 + 4 * n_inter + 2; return true; }
-    if (sscanf(id, "U32ArithmeticGate { num_ops: %u", &a) == 1) { g.kind = G_U32_ARITHMETIC; g.p[0] = a; g.num_constraints = 36 * a; return true; }
-    if (sscanf(id, "U32AddManyGate { num_addends: %u, num_ops: %u", &a, &b) == 2) { g.kind = G_U32_ADD_MANY; g.p[0] = a; g.p[1] = b; g.num_constraints = 21 * b; return true; }
-    if (sscanf(id, "U32SubtractionGate { num_ops: %u", &a) == 1) { g.kind = G_U32_SUBTRACTION; g.p[0] = a; g.num_constraints = 19 * a; return true; }
-    if (sscanf(id, "U32RangeCheckGate { num_input_limbs: %u", &a) == 1) { g.kind = G_U32_RANGE_CHECK; g.p[0] = a; g.num_constraints = 17 * a; return true; }
-    if (sscanf(id, "U32InterleaveGate { num_ops: %u", &a) == 1) { g.kind = G_U32_INTERLEAVE; g.p[0] = a; g.num_constraints = 34 * a; return true; }
-    if (sscanf(id, "UninterleaveToU32Gate { num_ops: %u", &a) == 1) { g.kind = G_UNINTERLEAVE_U32; g.p[0] = a; g.num_constraints = 67 * a; return true; }
-    if (sscanf(id, "UninterleaveToB32Gate { num_ops: %u", &a) == 1) { g.kind = G_UNINTERLEAVE_B32; g.p[0] = a; g.num_constraints = 67 * a; return true; }
-    if (sscanf(id, "ComparisonGate { num_bits: %u, num_chunks: %u", &a, &b) == 2) {
-        if (b == 0) return false;
-        unsigned cb = (a + b - 1) / b; if (cb > 6) return false;
-        g.kind = G_COMPARISON; g.p[0] = a; g.p[1] = b; g.num_constraints = 6 + 5 * b + cb; return true; }
-    return false;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fiat-Shamir challenger (host).  Semantics: gnark-plonky2-verifier/challenger/challenger.go:42-165.
-// ------------------------------------------------------------------------------------------------
-struct Challenger {
-    u64 st[12]; u64 in[8]; int nin; u64 out[8]; int nout;
-    Challenger() { memset(this, 0, sizeof *this); }
-    void duplex() {
-        for (int i = 0; i < nin; i++) st[i] = in[i];
-        nin = 0; poseidon_permute(st);
-        for (int i = 0; i < 8; i++) out[i] = st[i];
-        nout = 8;
-    }
-    void observe(u64 x) { nout = 0; in[nin++] = x; if (nin == 8) duplex(); }
-    void observe_n(const u64 *x, size_t n) { for (size_t i = 0; i < n; i++) observe(x[i]); }
-    void observe_ext(gl2 e) { observe(e.a); observe(e.b); }
-    // a Merkle/sponge hash of C::Hasher: 4 elements (Poseidon-GL) or 5 x 56-bit limbs (Poseidon-BN128)
-    void observe_hash(const u64 h[4], int hasher) {
-        if (hasher == HASHER_BN254) { u64 v[5]; bn254_to_vec_host(h, v); observe_n(v, 5); }
-        else observe_n(h, 4);
-    }
-    void observe_cap(const u64 *cap, size_t n_hashes, int hasher) { for (size_t i = 0; i < n_hashes; i++) observe_hash(cap + 4 * i, hasher); }
-    u64 get() { if (nin || !nout) duplex(); return out[--nout]; }
-    gl2 get_ext() { gl2 r; r.a = get(); r.b = get(); return r; }
-};
+#include "host_common.h"
 
 // ------------------------------------------------------------------------------------------------
 struct b200_circuit {
