@@ -44,7 +44,7 @@ def test_c_gate_matches_python(gid):
         assert k == len(ref) == g.num_constraints()
         assert [int(x) for x in out[:k]] == ref
 
-@pytest.mark.parametrize("kind,db", [("sig", 8), ("rec", 6)])
+@pytest.mark.parametrize("kind,db", [("sig", 8), ("rec", 6), ("sha", 7)])
 def test_workload_rows_satisfy_gates(kind, db):
     from b200_plonky2 import workloads
     from oracle import poseidon_gl as pgl, proof_io as io

@@ -70,3 +70,42 @@ def test_lde_is_low_degree_extension_property(ctx):
     _, ls, _ = ctx.lde_commit(s, log_n, 3, 4, want_coeffs=False)
     ref = np.array((la.astype(object) + lb.astype(object)) % P, dtype=np.uint64)
     assert np.array_equal(ls, ref)
+
+
+@pytest.mark.parametrize("log_n", [18, 20, 21, 22, 24])
+def test_ntt_large_sizes_three_pass_path(ctx, log_n):
+    """BASELINE config 5 sizes (2^16..2^24): transforms above 2^20 take three kernel passes.  Exact vs the oracle on one
+    column plus the size-independent round trip."""
+    from oracle import cbind
+    v = rand_field((1, 1 << log_n), 900 + log_n)
+    f = ctx.ntt_batch(v, log_n, inverse=False)
+    assert np.array_equal(f, cbind.ntt_batch(v, log_n, False))
+    assert np.array_equal(ctx.ntt_batch(f, log_n, inverse=True), v)
+
+def test_ntt_linearity_at_scale(ctx):
+    log_n = 19
+    a = rand_field((2, 1 << log_n), 1); b = rand_field((2, 1 << log_n), 2)
+    s = np.array((a.astype(object) + b.astype(object)) % P, dtype=np.uint64)
+    fa, fb, fs = ctx.ntt_batch(a, log_n), ctx.ntt_batch(b, log_n), ctx.ntt_batch(s, log_n)
+    assert np.array_equal(fs, np.array((fa.astype(object) + fb.astype(object)) % P, dtype=np.uint64))
+
+@pytest.mark.parametrize("log_len,ab", [(8, 4), (12, 4), (7, 3), (6, 2), (5, 1)])
+def test_fri_fold_matches_verifier_interpolation(ctx, log_len, ab):
+    """b200_fri_fold == the verifier's compute_evaluation (gnark-plonky2-verifier/fri/fri.go:244-316) on every coset."""
+    import ctypes
+    from b200_plonky2 import lib, c_void_p
+    from oracle import gl, verifier
+    n = 1 << log_len
+    vals = rand_field((n, 2), 77 + log_len)
+    beta = (123456789012345, 987654321098765); shift = pow(7, 1 << 4, gl.P)
+    out = np.zeros((n >> ab, 2), dtype=np.uint64)
+    b = (ctypes.c_uint64 * 2)(*beta)
+    rc = lib.b200_fri_fold(ctx.h, vals.ctypes.data_as(c_void_p), log_len, ab, b, ctypes.c_uint64(shift), out.ctypes.data_as(c_void_p))
+    assert rc == 0
+    w = gl.primitive_root_of_unity(log_len)
+    for i in range(0, n >> ab, max(1, (n >> ab) // 16)):
+        evals = [(int(vals[(i << ab) + k][0]), int(vals[(i << ab) + k][1])) for k in range(1 << ab)]
+        x_index = i << ab                                   # first point of the coset
+        x = shift * pow(w, gl.reverse_bits(x_index, log_len), gl.P) % gl.P
+        exp = verifier.compute_evaluation(x, 0, ab, evals, beta)
+        assert (int(out[i][0]), int(out[i][1])) == exp

@@ -25,7 +25,7 @@ def _prove_both(ctx, kind, db, seed):
     cpu = oc.prove(cd.wires, cd.public_inputs)
     return cd, oc, gpu, cpu
 
-@pytest.mark.parametrize("kind,db", [("tiny", 2), ("tiny", 3), ("tiny_pi", 4), ("tiny", 5), ("tiny_pi", 6), ("rec", 6), ("sig", 8), ("rec", 9), ("sig", 10), ("rec", 12), ("sig", 13)])
+@pytest.mark.parametrize("kind,db", [("tiny", 2), ("tiny", 3), ("tiny_pi", 4), ("tiny", 5), ("tiny_pi", 6), ("rec", 6), ("sig", 8), ("rec", 9), ("sig", 10), ("rec", 12), ("sig", 13), ("sha", 7), ("sha", 11)])
 def test_gpu_proof_bytes_equal_oracle_and_verify(ctx, kind, db):
     from oracle import prover, proof_io as io, verifier
     cd, oc, gpu, cpu = _prove_both(ctx, kind, db, seed=11)

@@ -12,7 +12,7 @@ def test_circuit_digest_formula_matches_golden_wrapper():
     assert prover.circuit_digest_bn254(cap, 12) == int(vd["circuit_digest"])
     assert int(vd["circuit_digest"]) == 15612857049394414280467902980451102556370837276268678037246302844075472795365
 
-@pytest.mark.parametrize("kind,db", [("sig", 8), ("rec", 6), ("rec", 9), ("tiny", 2), ("tiny", 3), ("tiny_pi", 5), ("tiny", 6)])
+@pytest.mark.parametrize("kind,db", [("sig", 8), ("rec", 6), ("rec", 9), ("tiny", 2), ("tiny", 3), ("tiny_pi", 5), ("tiny", 6), ("sha", 7)])
 def test_oracle_prover_accepted_by_oracle_verifier(kind, db):
     from b200_plonky2 import workloads
     cd = workloads.build(kind, db, seed=5)

@@ -58,6 +58,7 @@ _sig("b200_lde_commit_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c
 _sig("b200_poseidon_merkle", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p, c_void_p)
 _sig("b200_poseidon_merkle_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p)
 _sig("b200_poseidon_permute", c_int, c_void_p, c_void_p, c_size_t)
+_sig("b200_fri_fold", c_int, c_void_p, c_void_p, c_u32, c_u32, c_void_p, c_u64, c_void_p)
 _sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
 _sig("b200_verify_error", ctypes.c_char_p)
 

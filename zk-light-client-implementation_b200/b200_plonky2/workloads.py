@@ -61,6 +61,27 @@ def rec_circuit(degree_bits, seed=0, num_public_inputs=4):
     cb.fill_coset_interpolation(b, rng, c[10])
     return b, None
 
+def sha_circuit(degree_bits, seed=0, num_public_inputs=8):
+    """sha256_proof_u32-shaped circuit (near_bft_finality/src/prove_crypto/sha256.rs:62-84, crypto/plonky2_sha256_u32):
+    standard_recursion_config (135 wires) with the u32 interleave / uninterleave / add-many / arithmetic gates the
+    interleave-trick SHA-256 uses, digest words as public inputs."""
+    cfg = cb.CircuitConfig.standard_recursion_config()
+    rng = np.random.default_rng(seed)
+    b = cb.CircuitBuilder(cfg)
+    b.register_public_inputs([int(x) for x in rng.integers(0, 1 << 32, size=num_public_inputs)])
+    budget = (1 << degree_bits) - b.num_rows - 4
+    assert budget > 20
+    c = _mix(budget, [25, 20, 20, 15, 8, 6, 4, 2])
+    cb.fill_u32_interleave(b, rng, c[0])
+    cb.fill_uninterleave(b, rng, c[1], False)
+    cb.fill_uninterleave(b, rng, c[2], True)
+    cb.fill_u32_add_many(b, rng, c[3], 4)
+    cb.fill_u32_arithmetic(b, rng, c[4])
+    cb.fill_u32_range_check(b, rng, c[5], 4)
+    cb.fill_arithmetic(b, rng, c[6])
+    cb.fill_constant(b, rng.integers(0, 1 << 62, size=(c[7], 2), dtype=np.uint64))
+    return b, None
+
 def tiny_circuit(degree_bits, seed=0, num_public_inputs=0):
     """edge-case circuit: 2^degree_bits rows (>= 4) of arithmetic / constant gates, optional public inputs; small enough
     that FRI has no reduction layer (degree_bits <= 5)."""
@@ -80,6 +101,7 @@ def build(kind, degree_bits, seed=0, hasher="gl"):
     """kind: "sig" | "rec"; hasher "bn254" = PoseidonBN128GoldilocksConfig (the final wrap proof, prove_block.rs:279-300)."""
     if kind == "tiny": b, _ = tiny_circuit(degree_bits, seed)
     elif kind == "tiny_pi": b, _ = tiny_circuit(degree_bits, seed, 3)
+    elif kind == "sha": b, _ = sha_circuit(degree_bits, seed)
     else: b, _ = (sig_circuit if kind == "sig" else rec_circuit)(degree_bits, seed)
     cd = b.build()
     cd.common["hasher"] = hasher

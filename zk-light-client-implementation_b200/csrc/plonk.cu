@@ -389,13 +389,3 @@ void launch_pow(const u64 state[12], int pos, u64 start, u64 count, int bits, u6
     k_pow<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(b, pos, start, count, bits, (unsigned long long *)d_result);
     LAUNCHED(1);
 }
-
-// dst[c] = src[c * stride + index]
-__global__ void k_gather(const u64 *__restrict__ src, size_t stride, size_t count, size_t index, u64 *__restrict__ dst) {
-    size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (c < count) dst[c] = src[c * stride + index];
-}
-void launch_gather(const u64 *d_src, size_t src_stride, size_t count, size_t index, u64 *d_dst, cudaStream_t st) {
-    k_gather<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_src, src_stride, count, index, d_dst);
-    LAUNCHED(1);
-}

@@ -43,4 +43,3 @@ void launch_fri_combine(const FriCombineArgs &a, cudaStream_t st);
 void launch_fri_fold(const gl2 *d_in, gl2 *d_out, int log_len, int arity_bits, gl2 beta, u64 shift, const u64 *tw_fwd, cudaStream_t st);
 // proof of work: smallest candidate in [start, start+count) whose response has `bits` leading zeros, else ~0
 void launch_pow(const u64 state[12], int pos, u64 start, u64 count, int bits, u64 *d_result, cudaStream_t st);
-void launch_gather(const u64 *d_src, size_t src_stride, size_t count, size_t index, u64 *d_dst, cudaStream_t st);
