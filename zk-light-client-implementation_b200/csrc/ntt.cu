@@ -215,7 +215,35 @@ __global__ void k_bitrev_permute(const u64 *in, u64 *out, int L, size_t total) {
     size_t it = idx >> L; u32 i = (u32)(idx & ((size_t(1) << L) - 1));
     out[(it << L) + bitrev32(i, L)] = in[idx];
 }
+// tiled variant for L >= 10: index = hi(5) | mid | lo(5); the 32x32 tile (hi, lo) of a fixed mid lands at (rev lo, rev hi) of
+// rev(mid): both the load (over lo) and the store (over rev hi) touch 256-byte runs.
+__global__ void __launch_bounds__(256) k_bitrev_tiled(const u64 *__restrict__ in, u64 *__restrict__ out, int L, size_t tiles_per_item) {
+    __shared__ u64 tile[32][33];
+    const size_t it = blockIdx.x / tiles_per_item;
+    const u32 mid = (u32)(blockIdx.x % tiles_per_item);
+    const int mbits = L - 10;
+    const u64 *src = in + (it << L); u64 *dst = out + (it << L);
+    const u32 lane = threadIdx.x & 31, row0 = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u32 hi = row0 + 8 * k;
+        tile[hi][lane] = src[((size_t)hi << (L - 5)) | ((size_t)mid << 5) | lane];
+    }
+    __syncthreads();
+    const u32 rmid = bitrev32(mid, mbits);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u32 r = row0 + 8 * k;                                   // r = rev(lo), lane = rev(hi)
+        dst[((size_t)r << (L - 5)) | ((size_t)rmid << 5) | lane] = tile[bitrev32(lane, 5)][bitrev32(r, 5)];
+    }
+}
 void bitrev_permute(const u64 *in, u64 *out, int L, size_t items, cudaStream_t st) {
+    if (L >= 10) {
+        size_t tiles = size_t(1) << (L - 10);
+        k_bitrev_tiled<<<(unsigned)(items * tiles), 256, 0, st>>>(in, out, L, tiles);
+        LAUNCHED(1);
+        return;
+    }
     size_t total = items << L;
     k_bitrev_permute<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, L, total);
     LAUNCHED(1);
