@@ -12,6 +12,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build the product library and the oracle once
+    if not os.path.exists(os.path.join(PKG, "libb200plonky2.so")):
+        import __graft_entry__
+        __graft_entry__.build()
 
 @pytest.fixture(scope="session")
 def golden_dir():
