@@ -18,7 +18,8 @@
 struct CudaErr { cudaError_t e; const char *file; int line; };
 #define CUDA_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) throw CudaErr{_e, __FILE__, __LINE__}; } while (0)
 
-extern unsigned long long g_b200_launches;     // kernels launched by this library (process-wide)
+#include <atomic>
+extern std::atomic<unsigned long long> g_b200_launches;     // kernels launched by this library (process-wide)
 #define LAUNCHED(n) do { g_b200_launches += (n); CUDA_TRY(cudaGetLastError()); } while (0)
 
 struct DevBuf {   // RAII device buffer

@@ -6,7 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-unsigned long long g_b200_launches = 0;
+std::atomic<unsigned long long> g_b200_launches{0};
 
 int ctx_fail(b200_ctx *ctx, int code, const std::string &msg) { if (ctx) ctx->err = msg; return code; }
 
@@ -67,7 +67,7 @@ int b200_ctx_synchronize(b200_ctx *ctx) {
 
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void b200_free(void *p) { free(p); }
-uint64_t b200_kernel_launches(const b200_ctx *) { return g_b200_launches; }
+uint64_t b200_kernel_launches(const b200_ctx *) { return g_b200_launches.load(); }
 
 int b200_ctx_enable_timing(b200_ctx *ctx, int enable) {
     API_BEGIN(ctx)
