@@ -44,6 +44,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     for (auto &kv : ctx->lde_scale) cudaFree(kv.second);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -19,6 +19,7 @@ struct b200_ctx {
     std::string err;
     void *arena = nullptr; size_t arena_bytes = 0;   // grow-only scratch for b200_prove
     u64 *tmp_q_big = nullptr;
+    void *pinned = nullptr;                           // pinned staging for the small per-proof transfers
     cudaStream_t copy_stream = nullptr;               // H2D of host witnesses, overlapped with the LDE
     // optional phase timing (b200_ctx_enable_timing): CUDA events on the context stream around prover phases
     bool timing = false;

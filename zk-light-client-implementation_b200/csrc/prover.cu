@@ -42,6 +42,34 @@ struct Arena {      // bump allocator over one device allocation, reset per prov
 };
 static u8 *ctx_arena(b200_ctx *ctx, size_t bytes);   // defined below (grow-only scratch owned by the context)
 
+// Small host<->device transfers go through one pinned staging buffer per context: copies to/from pageable memory are
+// synchronous and staged by the driver (tens of microseconds each, ~15 per proof), which matters for the small
+// recursion-shaped proofs whose whole prove() takes a few milliseconds.
+struct Staging {
+    b200_ctx *ctx; cudaStream_t st; size_t off = 0;
+    struct Pending { void *dst; const void *src; size_t bytes; };
+    std::vector<Pending> pending;
+    static constexpr size_t CAP = size_t(8) << 20;
+    Staging(b200_ctx *c) : ctx(c), st(c->stream) {
+        if (!ctx->pinned) CUDA_TRY(cudaMallocHost(&ctx->pinned, CAP));
+    }
+    u8 *take(size_t bytes) { size_t b = (bytes + 63) & ~size_t(63); if (off + b > CAP) { sync(); off = 0; } if (b > CAP) throw ApiErr{B200_ERR_OOM, "staging buffer too small"}; u8 *p = (u8 *)ctx->pinned + off; off += b; return p; }
+    void d2h(void *dst, const void *dsrc, size_t bytes) {
+        u8 *p = take(bytes);
+        CUDA_TRY(cudaMemcpyAsync(p, dsrc, bytes, cudaMemcpyDeviceToHost, st));
+        pending.push_back({dst, p, bytes});
+    }
+    void h2d(void *ddst, const void *src, size_t bytes) {
+        u8 *p = take(bytes); memcpy(p, src, bytes);
+        CUDA_TRY(cudaMemcpyAsync(ddst, p, bytes, cudaMemcpyHostToDevice, st));
+    }
+    void sync() {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (auto &q : pending) memcpy(q.dst, q.src, q.bytes);
+        pending.clear();
+    }
+};
+
 static void put_u64(std::vector<uint8_t> &o, u64 x) { for (int i = 0; i < 8; i++) o.push_back((uint8_t)(x >> (8 * i))); }
 static void put_words(std::vector<uint8_t> &o, const u64 *w, size_t n) { for (size_t i = 0; i < n; i++) put_u64(o, w[i]); }
 
@@ -96,6 +124,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)); // openings tables
     need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
     Arena A; A.base = ctx_arena(ctx, need + (1 << 20)); A.cap = need + (1 << 20);
+    Staging S(ctx);
 
     // ---- public input hash, wires commitment ----
     u64 pi_hash[4]; poseidon_hash_no_pad_host(pis, n_pis, pi_hash);
@@ -128,8 +157,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         cudaEventDestroy(start_ev);
     }
     std::vector<u64> cap_w(capw), cap_z(capw), cap_q(capw);
-    CUDA_TRY(cudaMemcpyAsync(cap_w.data(), w_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    S.d2h(cap_w.data(), w_dig + dig_u64 - capw, capw * 8);
+    S.sync();
 
     Challenger ch;
     ch.observe_hash(k->digest, HS); ch.observe_n(pi_hash, 4); ch.observe_cap(cap_w.data(), ncap, HS);
@@ -144,9 +173,9 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     launch_partial_products(d_wires, k->sigma_values.u(), k->d_kis.u(), nlog, R, npp, qdf, nch, betas, gammas, ctx->tw.fwd, zs_vals, pp_scratch, d_final_prod, st); }
     commit_values(ctx, zs_vals, nzp, nlog, rb, chh, zs_coeffs, zs_lde, zs_dig, HS);
     u64 final_prod[MAX_CHALLENGES];
-    CUDA_TRY(cudaMemcpyAsync(cap_z.data(), zs_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(final_prod, d_final_prod, nch * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    S.d2h(cap_z.data(), zs_dig + dig_u64 - capw, capw * 8);
+    S.d2h(final_prod, d_final_prod, nch * 8);
+    S.sync();
     for (u32 i = 0; i < nch; i++) if (final_prod[i] != 1) throw ApiErr{B200_ERR_UNSATISFIED, "permutation argument: grand product != 1 (copy constraints violated)"};
     if (dbg) dump_dev(dbg, "zs_pp_values.bin", zs_vals, (size_t)nzp * n * 8, st);
     ch.observe_cap(cap_z.data(), ncap, HS);
@@ -159,7 +188,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         std::vector<u64> apow((size_t)MAX_CHALLENGES * apow_stride, 0);
         for (u32 c = 0; c < nch; c++) { u64 p = 1; for (u32 i = 0; i < apow_stride; i++) { apow[(size_t)c * apow_stride + i] = p; p = gl_mul(p, alphas[c]); } }
         u64 *d_apow = A.take(apow.size());
-        CUDA_TRY(cudaMemcpyAsync(d_apow, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, st));
+        S.h2d(d_apow, apow.data(), apow.size() * 8);
         u64 *q_vals = A.take((size_t)nch * N), *q_big = A.take((size_t)nch * N);
         QuotientArgs qa; memset(&qa, 0, sizeof qa);
         qa.cs_lde = k->cs_lde.u(); qa.wires_lde = w_lde; qa.zs_lde = zs_lde; qa.out = q_vals;
@@ -185,8 +214,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     u64 *q_coeffs = A.take((size_t)nq * n), *q_lde = A.take((size_t)nq * N), *q_dig = A.take(dig_u64);
     launch_quotient_split(ctx->tmp_q_big, q_coeffs, nlog, rb, nch, st);
     commit_coeffs(ctx, q_coeffs, nq, nlog, rb, chh, q_lde, q_dig, HS);
-    CUDA_TRY(cudaMemcpyAsync(cap_q.data(), q_dig + dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    S.d2h(cap_q.data(), q_dig + dig_u64 - capw, capw * 8);
+    S.sync();
     if (dbg) dump_dev(dbg, "quotient_coeffs_br.bin", q_coeffs, (size_t)nq * n * 8, st);
     ch.observe_cap(cap_q.data(), ncap, HS);
     gl2 zeta = ch.get_ext();
@@ -212,8 +241,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         launch_eval_polys(zs_coeffs, nch, nlog, d_tab2, d_open + off, st);
     }
     std::vector<gl2> open(total_polys + nch);
-    CUDA_TRY(cudaMemcpyAsync(open.data(), d_open, open.size() * sizeof(gl2), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    S.d2h(open.data(), d_open, open.size() * sizeof(gl2));
+    S.sync();
     for (size_t i = 0; i < total_polys; i++) ch.observe_ext(open[i]);
     for (u32 i = 0; i < nch; i++) ch.observe_ext(open[total_polys + i]);
 
@@ -225,7 +254,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     for (size_t i = 0; i < total_polys; i++) y0 = gl2_add(y0, gl2_mul(open[i], apow[i]));
     for (u32 i = 0; i < nch; i++) y1 = gl2_add(y1, gl2_mul(open[total_polys + i], apow[i]));
     gl2 *d_apow2 = (gl2 *)A.take(2 * total_polys);
-    CUDA_TRY(cudaMemcpyAsync(d_apow2, apow.data(), total_polys * sizeof(gl2), cudaMemcpyHostToDevice, st));
+    S.h2d(d_apow2, apow.data(), total_polys * sizeof(gl2));
     gl2 *fri_a = (gl2 *)A.take(2 * N), *fri_b = (gl2 *)A.take(2 * N);
     {
         FriCombineArgs fa; memset(&fa, 0, sizeof fa);
@@ -251,8 +280,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         if (HS == HASHER_BN254) { merkle_leaves_rowmajor_bn254((const u64 *)cur, size_t(2) << ab, Ly.log_leaves, Ly.dig, st); merkle_build_bn254(Ly.dig, Ly.log_leaves, chh, st); }
         else { merkle_leaves_rowmajor((const u64 *)cur, size_t(2) << ab, Ly.log_leaves, Ly.dig, st); merkle_build(Ly.dig, Ly.log_leaves, chh, st); }
         std::vector<u64> cap(capw);
-        CUDA_TRY(cudaMemcpyAsync(cap.data(), Ly.dig + Ly.dig_u64 - capw, capw * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        S.d2h(cap.data(), Ly.dig + Ly.dig_u64 - capw, capw * 8);
+        S.sync();
         ch.observe_cap(cap.data(), ncap, HS);
         gl2 beta = ch.get_ext();
         fri_betas.push_back(beta); layer_caps.push_back(cap); layers.push_back(Ly);
@@ -264,8 +293,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     // final polynomial (host): values on shift * H_{2^cur_log} in bit-reversed order -> coefficients
     size_t fin_n = size_t(1) << cur_log;
     std::vector<gl2> fin_vals(fin_n);
-    CUDA_TRY(cudaMemcpyAsync(fin_vals.data(), cur, fin_n * sizeof(gl2), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    S.d2h(fin_vals.data(), cur, fin_n * sizeof(gl2));
+    S.sync();
     std::vector<u64> fa(fin_n), fb(fin_n);
     for (size_t i = 0; i < fin_n; i++) { size_t r = bitrev32((u32)i, cur_log); fa[i] = fin_vals[r].a; fb[i] = fin_vals[r].b; }
     host_ntt(fa, cur_log, true); host_ntt(fb, cur_log, true);
@@ -284,15 +313,16 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         if (pow_hint && pow_hint < GL_P && (response(pow_hint) >> (64 - k->pow_bits)) == 0) pow_witness = pow_hint;
         PhaseTimer tp(ctx, "pow");
         u64 *d_res = A.take(8);
-        u64 start = 0; const u64 chunk = u64(1) << 18;   // expected 2^16 trials for a 16-bit PoW
+        u64 start = 0; u64 chunk = u64(1) << (k->pow_bits + 1 < 24 ? k->pow_bits + 1 : 24);   // ~86 % hit rate per first launch
         while (pow_witness == ~u64(0)) {
             u64 init = ~u64(0);
-            CUDA_TRY(cudaMemcpyAsync(d_res, &init, 8, cudaMemcpyHostToDevice, st));
+            S.h2d(d_res, &init, 8);
             launch_pow(base_state, pos, start, chunk, (int)k->pow_bits, d_res, st);
-            u64 res; CUDA_TRY(cudaMemcpyAsync(&res, d_res, 8, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            u64 res; S.d2h(&res, d_res, 8);
+            S.sync();
             if (res != ~u64(0)) pow_witness = res;
             start += chunk;
+            if (chunk < (u64(1) << 22)) chunk <<= 1;
             if (start > (u64(1) << 40)) throw ApiErr{B200_ERR_CUDA, "proof of work not found"};
         }
         ch.observe(pow_witness);
@@ -329,11 +359,11 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         PhaseTimer tq(ctx, "query_gather");
         CopyDesc *d_descs = (CopyDesc *)A.take(descs.size() * sizeof(CopyDesc) / 8 + 8);
         u64 *d_q = A.take(dst + 8);
-        CUDA_TRY(cudaMemcpyAsync(d_descs, descs.data(), descs.size() * sizeof(CopyDesc), cudaMemcpyHostToDevice, st));
+        S.h2d(d_descs, descs.data(), descs.size() * sizeof(CopyDesc));
         k_copy_descs<<<(unsigned)descs.size(), 64, 0, st>>>(d_descs, d_q);
         LAUNCHED(1);
-        CUDA_TRY(cudaMemcpyAsync(qdata.data(), d_q, (size_t)dst * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        S.d2h(qdata.data(), d_q, (size_t)dst * 8);
+        S.sync();
     }
 
     // ---- serialize (ProofWithPublicInputs::to_bytes layout) ----
