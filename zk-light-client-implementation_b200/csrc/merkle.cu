@@ -37,7 +37,6 @@ __global__ void __launch_bounds__(MK_THREADS) k_leaves_colmajor(const u64 *__res
     }
 }
 
-template <int U>
 __global__ void __launch_bounds__(MK_THREADS) k_leaves_rowmajor(const u64 *__restrict__ data, size_t width, size_t L, u64 *__restrict__ digests) {
     __shared__ u64 sm[12 * MK_THREADS];
     size_t leaf = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -52,7 +51,7 @@ __global__ void __launch_bounds__(MK_THREADS) k_leaves_rowmajor(const u64 *__res
         for (size_t c = 0; c < width; c += 8) {
 #pragma unroll
             for (int j = 0; j < 8; j++) if (c + j < width) ST(j) = row[c + j];
-            poseidon_permute_smem_t<U>(&ST(0), MK_THREADS);
+            poseidon_permute_smem(&ST(0), MK_THREADS);
         }
     }
     if (active) {
@@ -61,7 +60,6 @@ __global__ void __launch_bounds__(MK_THREADS) k_leaves_rowmajor(const u64 *__res
     }
 }
 
-template <int U>
 __global__ void __launch_bounds__(MK_THREADS) k_merkle_level(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n_out) {
     __shared__ u64 sm[12 * MK_THREADS];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -71,7 +69,7 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_level(const u64 *__restri
     ulonglong2 a = p[0], b = p[1], c = p[2], d = p[3];
     ST(0) = a.x; ST(1) = a.y; ST(2) = b.x; ST(3) = b.y; ST(4) = c.x; ST(5) = c.y; ST(6) = d.x; ST(7) = d.y;
     ST(8) = 0; ST(9) = 0; ST(10) = 0; ST(11) = 0;
-    poseidon_permute_smem_t<U>(&ST(0), MK_THREADS);
+    poseidon_permute_smem(&ST(0), MK_THREADS);
     if (active) {
         ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + 4 * i);
         o[0] = make_ulonglong2(ST(0), ST(1)); o[1] = make_ulonglong2(ST(2), ST(3));
@@ -85,8 +83,7 @@ void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digest
 }
 void merkle_leaves_rowmajor(const u64 *data, size_t width, int log_L, u64 *digests, cudaStream_t st) {
     size_t L = size_t(1) << log_L;
-    if (L <= (size_t)148 * 4 * MK_THREADS) k_leaves_rowmajor<12><<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, width, L, digests);
-    else k_leaves_rowmajor<2><<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, width, L, digests);
+    k_leaves_rowmajor<<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, width, L, digests);
     LAUNCHED(1);
 }
 void merkle_build(u64 *digests, int log_L, int cap_height, cudaStream_t st) {
@@ -94,9 +91,7 @@ void merkle_build(u64 *digests, int log_L, int cap_height, cudaStream_t st) {
     for (int lv = log_L; lv > cap_height; lv--) {
         size_t n = size_t(1) << lv;
         u64 *nxt = cur + 4 * n;
-        // levels that cannot fill the machine are latency-bound: use the ILP-12 variant there
-        if (n / 2 <= (size_t)148 * 4 * MK_THREADS) k_merkle_level<12><<<(unsigned)((n / 2 + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(cur, nxt, n / 2);
-        else k_merkle_level<2><<<(unsigned)((n / 2 + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(cur, nxt, n / 2);
+        k_merkle_level<<<(unsigned)((n / 2 + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(cur, nxt, n / 2);
         LAUNCHED(1);
         cur = nxt;
     }

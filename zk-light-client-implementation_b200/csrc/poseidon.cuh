@@ -242,34 +242,21 @@ GL_HD void poseidon_two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
 // the textbook form (S-box on word 0, all 12 round constants, full MDS) because with the multiplier-free MDS that is
 // cheaper than the "fast" sparse-matrix form (23 modmuls) and needs no extra tables.  Same permutation, bit-exact.
 // ---------------------------------------------------------------------------------------------------------------
-// U = unroll factor of the S-box loop: 2 for the throughput-bound leaf kernels (smallest code), 12 for the small,
-// latency-bound launches (upper Merkle levels, FRI trees): twelve independent multiplication chains in flight.
-template <int U>
-static __device__ __noinline__ void poseidon_permute_smem_t(u64 *st, const int stride) {
+static __device__ __noinline__ void poseidon_permute_smem(u64 *st, const int stride) {
     for (int r = 0; r < 30; r++) {
         const bool full = (r < 4) || (r >= 26);
         const u64 *rc = d_POSEIDON_RC + 12 * r;
         u64 s[12];
         if (full) {
-            if (U >= 12) {
-#pragma unroll
-                for (int i = 0; i < 12; i++) {
-                    u64 c = rc[i];
-                    u64 x = st[i * stride] + c;
-                    if (x < c) x += GL_EPS;
-                    s[i] = poseidon_sbox(x);
-                }
-            } else {
 #pragma unroll 2
-                for (int i = 0; i < 12; i++) {
-                    u64 c = rc[i];
-                    u64 x = st[i * stride] + c;
-                    if (x < c) x += GL_EPS;
-                    st[i * stride] = poseidon_sbox(x);
-                }
-#pragma unroll
-                for (int i = 0; i < 12; i++) s[i] = st[i * stride];
+            for (int i = 0; i < 12; i++) {
+                u64 c = rc[i];
+                u64 x = st[i * stride] + c;
+                if (x < c) x += GL_EPS;
+                st[i * stride] = poseidon_sbox(x);
             }
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = st[i * stride];
         } else {
 #pragma unroll
             for (int i = 0; i < 12; i++) {
@@ -287,7 +274,6 @@ static __device__ __noinline__ void poseidon_permute_smem_t(u64 *st, const int s
 #pragma unroll
     for (int i = 0; i < 12; i++) st[i * stride] = gl_canon(st[i * stride]);
 }
-static __device__ __forceinline__ void poseidon_permute_smem(u64 *st, const int stride) { poseidon_permute_smem_t<2>(st, stride); }
 #endif
 
 // host-side sponge helpers (used by the challenger / public-input hash)
