@@ -141,6 +141,12 @@ size_t b200_merkle_num_u64(uint32_t log_L, uint32_t cap_height);
  * by beta; shift = coset shift of the layer (7^(arity^layer)).  out: 2^(log_len-arity_bits) ext values. */
 int b200_fri_fold(b200_ctx *ctx, const uint64_t *values, uint32_t log_len, uint32_t arity_bits, const uint64_t beta[2],
                   uint64_t shift, uint64_t *out);
+/* ---- Groth16 wrap (next row, SURVEY 8f-3 / BASELINE config 4): BN254 G1 multi-scalar multiplication ----
+ * (gnark-crypto ecc/bn254 MultiExp under groth16.Prove, gnark-plonky2-verifier/cmd/web-api.go:77)
+ * points: n affine points, 8 u64 each (x limbs, y limbs; little-endian, canonical, not Montgomery; all-zero = infinity);
+ * scalars: n x 4 u64 canonical (< r).  out_affine: 8 u64 (all-zero = infinity). */
+int b200_msm_g1(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[8]);
+int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[8]);
 /* Poseidon permutation of `count` independent 12-word states (self-test / throughput probe). */
 int b200_poseidon_permute(b200_ctx *ctx, uint64_t *states, size_t count);
 

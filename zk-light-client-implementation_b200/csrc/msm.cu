@@ -1,0 +1,273 @@
+// BN254 G1 multi-scalar multiplication (Pippenger bucket method) for sm_100a -- SURVEY.md section 8f rank 3 / BASELINE
+// config 4: the MSMs inside gnark's groth16.Prove (gnark-plonky2-verifier/cmd/web-api.go:77; gnark-crypto
+// v0.12.2-0.20231013160410-1f65e75b6dfb ecc/bn254 MultiExp, not vendored) that wrap the final plonky2 proof.
+// Result = sum_i scalars[i] * points[i] on y^2 = x^3 + 3 over F_q, returned in affine coordinates: a group element, so
+// bit-exact against any correct implementation (oracle/bn254_curve.py restates the textbook group law).
+//
+// Layout: points affine (x, y) = 8 u64 little-endian limbs, canonical (NOT Montgomery) -- the (0,0) encoding is the
+// point at infinity, as in gnark-crypto; scalars 4 u64 limbs canonical < r.  Window c = 16 bits, 16 windows.
+//   1. k_digits      : one thread per scalar, 16 digits, histogram per (window, bucket)               (reads 32 N bytes)
+//   2. k_scan        : exclusive scan of the 65536 bucket counts of each window
+//   3. k_scatter     : counting-sort the point indices by bucket
+//   4. k_buckets     : one thread per (window, bucket): XYZZ accumulator += affine point (8M + 2S)  (reads 64 B per digit)
+//   5. k_window_*    : per window sum_d d * B_d via chunked running sums, then Horner over the windows (host, 16 steps)
+// Algorithmic bytes: 64 N (points) + 32 N (scalars); the bucket phase re-reads every point 16 times through L2.
+#include "../../include/b200_plonky2.h"
+#include "ctx.h"
+#include <vector>
+
+namespace {
+
+struct fq { u64 v[4]; };
+#define Q0 0x3c208c16d87cfd47ULL
+#define Q1 0x97816a916871ca8dULL
+#define Q2 0xb85045b68181585dULL
+#define Q3 0x30644e72e131a029ULL
+#define Q_INV 0x87d20782e4866389ULL
+
+GL_HD u64 mac64(u64 a, u64 b, u64 c, u64 &carry) {
+    u64 lo, hi; gl_mul_wide(a, b, lo, hi);
+    lo += c; hi += (lo < c);
+    lo += carry; hi += (lo < carry);
+    carry = hi; return lo;
+}
+GL_HD bool fq_geq(const u64 a[4]) {
+    const u64 m[4] = {Q0, Q1, Q2, Q3};
+    for (int i = 3; i >= 0; i--) { if (a[i] > m[i]) return true; if (a[i] < m[i]) return false; }
+    return true;
+}
+GL_HD void fq_subq(u64 a[4]) {
+    const u64 m[4] = {Q0, Q1, Q2, Q3}; u64 br = 0;
+    for (int i = 0; i < 4; i++) { u64 d = a[i] - m[i]; u64 b1 = a[i] < m[i]; u64 d2 = d - br; u64 b2 = d < br; a[i] = d2; br = b1 | b2; }
+}
+GL_HD fq fq_add(const fq &a, const fq &b) {
+    fq r; u64 c = 0;
+    for (int i = 0; i < 4; i++) { u64 s = a.v[i] + b.v[i]; u64 c1 = s < a.v[i]; u64 s2 = s + c; u64 c2 = s2 < s; r.v[i] = s2; c = c1 | c2; }
+    if (c || fq_geq(r.v)) fq_subq(r.v);
+    return r;
+}
+GL_HD fq fq_sub(const fq &a, const fq &b) {
+    const u64 m[4] = {Q0, Q1, Q2, Q3};
+    fq r; u64 br = 0;
+    for (int i = 0; i < 4; i++) { u64 d = a.v[i] - b.v[i]; u64 b1 = a.v[i] < b.v[i]; u64 d2 = d - br; u64 b2 = d < br; r.v[i] = d2; br = b1 | b2; }
+    if (br) { u64 c = 0; for (int i = 0; i < 4; i++) { u64 s = r.v[i] + m[i]; u64 c1 = s < r.v[i]; u64 s2 = s + c; u64 c2 = s2 < s; r.v[i] = s2; c = c1 | c2; } }
+    return r;
+}
+#define FQ_FN static __host__ __device__ __noinline__
+FQ_FN fq fq_mul(const fq &a, const fq &b) {        // Montgomery CIOS
+    const u64 m[4] = {Q0, Q1, Q2, Q3};
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u64 c = 0;
+        for (int j = 0; j < 4; j++) t[j] = mac64(a.v[j], b.v[i], t[j], c);
+        { u64 s = t[4] + c; t[5] = s < c; t[4] = s; }
+        u64 qq = t[0] * Q_INV; c = 0;
+        (void)mac64(qq, m[0], t[0], c);
+        for (int j = 1; j < 4; j++) t[j - 1] = mac64(qq, m[j], t[j], c);
+        { u64 s = t[4] + c; u64 cc = s < c; t[3] = s; t[4] = t[5] + cc; }
+    }
+    fq r; for (int i = 0; i < 4; i++) r.v[i] = t[i];
+    if (t[4] || fq_geq(r.v)) fq_subq(r.v);
+    return r;
+}
+GL_HD fq fq_zero() { fq r; for (int i = 0; i < 4; i++) r.v[i] = 0; return r; }
+GL_HD bool fq_is_zero(const fq &a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
+GL_HD fq fq_to_mont(const u64 x[4]) {
+    const fq r2 = {{0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL}};
+    fq a; for (int i = 0; i < 4; i++) a.v[i] = x[i];
+    return fq_mul(a, r2);
+}
+GL_HD void fq_from_mont(const fq &a, u64 out[4]) { const fq one = {{1, 0, 0, 0}}; fq r = fq_mul(a, one); for (int i = 0; i < 4; i++) out[i] = r.v[i]; }
+GL_HD fq fq_one() { const fq o = {{0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL}}; return o; }
+
+static fq fq_inv_host(const fq &a) {      // Fermat, host only (final conversion to affine)
+    u64 e[4] = {Q0 - 2, Q1, Q2, Q3};
+    fq r = fq_one(), b = a;
+    for (int i = 0; i < 256; i++) { if ((e[i / 64] >> (i % 64)) & 1) r = fq_mul(r, b); b = fq_mul(b, b); }
+    return r;
+}
+
+struct xyzz { fq x, y, zz, zzz; };      // affine (x/zz, y/zzz); identity: zz == 0
+GL_HD xyzz pt_identity() { xyzz p; p.x = fq_zero(); p.y = fq_zero(); p.zz = fq_zero(); p.zzz = fq_zero(); return p; }
+GL_HD bool pt_is_identity(const xyzz &p) { return fq_is_zero(p.zz); }
+
+FQ_FN xyzz pt_double_affine(const fq &x, const fq &y) {     // dbl-2008-s-1 with ZZ = ZZZ = 1, a = 0
+    fq u = fq_add(y, y), v = fq_mul(u, u), w = fq_mul(u, v), s = fq_mul(x, v);
+    fq xx = fq_mul(x, x), m = fq_add(fq_add(xx, xx), xx);
+    xyzz r;
+    r.x = fq_sub(fq_mul(m, m), fq_add(s, s));
+    r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, y));
+    r.zz = v; r.zzz = w;
+    return r;
+}
+FQ_FN xyzz pt_double(const xyzz &p) {
+    if (pt_is_identity(p)) return p;
+    fq u = fq_add(p.y, p.y), v = fq_mul(u, u), w = fq_mul(u, v), s = fq_mul(p.x, v);
+    fq xx = fq_mul(p.x, p.x), m = fq_add(fq_add(xx, xx), xx);
+    xyzz r;
+    r.x = fq_sub(fq_mul(m, m), fq_add(s, s));
+    r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, p.y));
+    r.zz = fq_mul(v, p.zz); r.zzz = fq_mul(w, p.zzz);
+    return r;
+}
+FQ_FN void pt_madd(xyzz &a, const fq &x2, const fq &y2) {   // a += (x2, y2) affine (madd-2008-s)
+    if (pt_is_identity(a)) { a.x = x2; a.y = y2; a.zz = fq_one(); a.zzz = fq_one(); return; }
+    fq u2 = fq_mul(x2, a.zz), s2 = fq_mul(y2, a.zzz);
+    fq p = fq_sub(u2, a.x), r = fq_sub(s2, a.y);
+    if (fq_is_zero(p)) {
+        if (fq_is_zero(r)) a = pt_double_affine(x2, y2); else a = pt_identity();
+        return;
+    }
+    fq pp = fq_mul(p, p), ppp = fq_mul(p, pp), q = fq_mul(a.x, pp);
+    fq x3 = fq_sub(fq_sub(fq_mul(r, r), ppp), fq_add(q, q));
+    fq y3 = fq_sub(fq_mul(r, fq_sub(q, x3)), fq_mul(a.y, ppp));
+    a.x = x3; a.y = y3; a.zz = fq_mul(a.zz, pp); a.zzz = fq_mul(a.zzz, ppp);
+}
+FQ_FN void pt_add(xyzz &a, const xyzz &b) {                 // a += b (add-2008-s)
+    if (pt_is_identity(b)) return;
+    if (pt_is_identity(a)) { a = b; return; }
+    fq u1 = fq_mul(a.x, b.zz), u2 = fq_mul(b.x, a.zz), s1 = fq_mul(a.y, b.zzz), s2 = fq_mul(b.y, a.zzz);
+    fq p = fq_sub(u2, u1), r = fq_sub(s2, s1);
+    if (fq_is_zero(p)) {
+        if (fq_is_zero(r)) a = pt_double(a); else a = pt_identity();
+        return;
+    }
+    fq pp = fq_mul(p, p), ppp = fq_mul(p, pp), q = fq_mul(u1, pp);
+    fq x3 = fq_sub(fq_sub(fq_mul(r, r), ppp), fq_add(q, q));
+    fq y3 = fq_sub(fq_mul(r, fq_sub(q, x3)), fq_mul(s1, ppp));
+    a.x = x3; a.y = y3; a.zz = fq_mul(fq_mul(a.zz, b.zz), pp); a.zzz = fq_mul(fq_mul(a.zzz, b.zzz), ppp);
+}
+
+constexpr int WBITS = 16, NWIN = 16;            // 16 x 16 = 256 >= 254 scalar bits
+constexpr u32 NBUCKET = 1u << WBITS;
+
+__global__ void k_digits(const u64 *__restrict__ scalars, size_t n, u32 *__restrict__ digits, u32 *__restrict__ counts) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u64 w = scalars[4 * i + k];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            u32 d = (u32)(w >> (16 * j)) & 0xFFFFu;
+            int win = 4 * k + j;
+            digits[(size_t)win * n + i] = d;
+            if (d) atomicAdd(&counts[(size_t)win * NBUCKET + d], 1u);
+        }
+    }
+}
+__global__ void k_scan(const u32 *__restrict__ counts, u32 *__restrict__ offsets) {      // one block per window, 1024 threads x 64 buckets
+    __shared__ u32 part[1024];
+    const u32 *c = counts + (size_t)blockIdx.x * NBUCKET; u32 *o = offsets + (size_t)blockIdx.x * NBUCKET;
+    u32 base = threadIdx.x * 64, s = 0;
+    for (int k = 0; k < 64; k++) s += c[base + k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) { u32 t = threadIdx.x >= off ? part[threadIdx.x - off] : 0; __syncthreads(); part[threadIdx.x] += t; __syncthreads(); }
+    u32 run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (int k = 0; k < 64; k++) { o[base + k] = run; run += c[base + k]; }
+}
+__global__ void k_scatter(const u32 *__restrict__ digits, size_t n, const u32 *__restrict__ offsets, u32 *__restrict__ cursor, u32 *__restrict__ sorted) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= n * NWIN) return;
+    size_t win = idx / n, i = idx % n;
+    u32 d = digits[idx];
+    if (!d) return;
+    u32 pos = atomicAdd(&cursor[win * NBUCKET + d], 1u);
+    sorted[win * n + offsets[win * NBUCKET + d] + pos] = (u32)i;
+}
+__global__ void __launch_bounds__(128) k_buckets(const u64 *__restrict__ points, size_t n, const u32 *__restrict__ counts, const u32 *__restrict__ offsets,
+                                                 const u32 *__restrict__ sorted, xyzz *__restrict__ buckets) {
+    size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (b >= (size_t)NWIN * NBUCKET) return;
+    size_t win = b / NBUCKET;
+    xyzz acc = pt_identity();
+    u32 cnt = counts[b], off = offsets[b];
+    const u32 *idx = sorted + win * n + off;
+    for (u32 k = 0; k < cnt; k++) {
+        const u64 *p = points + 8 * (size_t)idx[k];
+        u64 xl[4] = {p[0], p[1], p[2], p[3]}, yl[4] = {p[4], p[5], p[6], p[7]};
+        if ((xl[0] | xl[1] | xl[2] | xl[3] | yl[0] | yl[1] | yl[2] | yl[3]) == 0) continue;     // point at infinity
+        pt_madd(acc, fq_to_mont(xl), fq_to_mont(yl));
+    }
+    buckets[b] = acc;
+}
+// chunked running sums: thread (win, chunk) covers buckets [start, start + CH)
+constexpr u32 CH = 256, NCHUNK = NBUCKET / CH;
+__global__ void __launch_bounds__(64) k_window_chunks(const xyzz *__restrict__ buckets, xyzz *__restrict__ chunk_acc) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NWIN * NCHUNK) return;
+    u32 win = t / NCHUNK, ch = t % NCHUNK, start = ch * CH;
+    const xyzz *B = buckets + (size_t)win * NBUCKET;
+    xyzz run = pt_identity(), acc = pt_identity();
+    for (int d = (int)(start + CH - 1); d >= (int)start; d--) {
+        if (d != 0) pt_add(run, B[d]);
+        pt_add(acc, run);
+    }
+    // acc = sum_d (d - start + 1) B_d ; wanted sum_d d B_d = acc + (start - 1) * run
+    if (start > 0) {
+        u32 k = start - 1;
+        xyzz kr = pt_identity(), base = run;
+        while (k) { if (k & 1) pt_add(kr, base); base = pt_double(base); k >>= 1; }
+        pt_add(acc, kr);
+    } else {
+        xyzz neg = run; neg.y = fq_sub(fq_zero(), run.y);
+        pt_add(acc, neg);
+    }
+    chunk_acc[t] = acc;
+}
+__global__ void k_window_final(const xyzz *__restrict__ chunk_acc, xyzz *__restrict__ out) {   // one thread per window sums its chunks
+    u32 win = blockIdx.x * blockDim.x + threadIdx.x;
+    if (win >= NWIN) return;
+    xyzz s = pt_identity();
+    for (u32 c = 0; c < NCHUNK; c++) pt_add(s, chunk_acc[win * NCHUNK + c]);
+    out[win] = s;
+}
+
+}  // namespace
+
+int ctx_fail(b200_ctx *ctx, int code, const std::string &msg);
+
+extern "C" int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[8]) {
+    if (!ctx) return B200_ERR_BAD_ARG;
+    try {
+        cudaSetDevice(ctx->device);
+        if (!d_points || !d_scalars || !out_affine || n == 0 || n > (size_t(1) << 28)) throw ApiErr{B200_ERR_BAD_ARG, "b200_msm_g1: bad arguments"};
+        cudaStream_t st = ctx->stream;
+        DevBuf digits(n * NWIN * 4), counts((size_t)NWIN * NBUCKET * 4), offsets((size_t)NWIN * NBUCKET * 4), cursor((size_t)NWIN * NBUCKET * 4),
+            sorted(n * NWIN * 4), buckets((size_t)NWIN * NBUCKET * sizeof(xyzz)), chunks((size_t)NWIN * NCHUNK * sizeof(xyzz)), wins(NWIN * sizeof(xyzz));
+        CUDA_TRY(cudaMemsetAsync(counts.p, 0, counts.bytes, st)); CUDA_TRY(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
+        k_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, (u32 *)digits.p, (u32 *)counts.p); LAUNCHED(1);
+        k_scan<<<NWIN, 1024, 0, st>>>((const u32 *)counts.p, (u32 *)offsets.p); LAUNCHED(1);
+        k_scatter<<<(unsigned)((n * NWIN + 255) / 256), 256, 0, st>>>((const u32 *)digits.p, n, (const u32 *)offsets.p, (u32 *)cursor.p, (u32 *)sorted.p); LAUNCHED(1);
+        k_buckets<<<(unsigned)(((size_t)NWIN * NBUCKET + 127) / 128), 128, 0, st>>>(d_points, n, (const u32 *)counts.p, (const u32 *)offsets.p, (const u32 *)sorted.p, (xyzz *)buckets.p); LAUNCHED(1);
+        k_window_chunks<<<(NWIN * NCHUNK + 63) / 64, 64, 0, st>>>((const xyzz *)buckets.p, (xyzz *)chunks.p); LAUNCHED(1);
+        k_window_final<<<1, 32, 0, st>>>((const xyzz *)chunks.p, (xyzz *)wins.p); LAUNCHED(1);
+        std::vector<xyzz> w(NWIN);
+        CUDA_TRY(cudaMemcpyAsync(w.data(), wins.p, NWIN * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        xyzz acc = pt_identity();                      // Horner over the windows on the host: sum_w 2^(16 w) S_w
+        for (int wi = NWIN - 1; wi >= 0; wi--) {
+            for (int k = 0; k < WBITS; k++) acc = pt_double(acc);
+            pt_add(acc, w[wi]);
+        }
+        if (pt_is_identity(acc)) { for (int i = 0; i < 8; i++) out_affine[i] = 0; return B200_OK; }
+        fq zi2 = fq_inv_host(acc.zz), zi3 = fq_inv_host(acc.zzz);
+        fq_from_mont(fq_mul(acc.x, zi2), out_affine); fq_from_mont(fq_mul(acc.y, zi3), out_affine + 4);
+        return B200_OK;
+    } catch (const CudaErr &e) {
+        char buf[256]; snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.e, cudaGetErrorString(e.e), e.file, e.line);
+        cudaGetLastError(); return ctx_fail(ctx, e.e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA, buf);
+    } catch (const ApiErr &e) { return ctx_fail(ctx, e.code, e.msg); }
+}
+
+extern "C" int b200_msm_g1(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[8]) {
+    if (!ctx || !points || !scalars || !n) return B200_ERR_BAD_ARG;
+    try {
+        cudaSetDevice(ctx->device);
+        DevBuf p(n * 64), s(n * 32);
+        CUDA_TRY(cudaMemcpyAsync(p.p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(s.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+        return b200_msm_g1_dev(ctx, p.u(), s.u(), n, out_affine);
+    } catch (const CudaErr &e) { return ctx_fail(ctx, B200_ERR_CUDA, "CUDA error in b200_msm_g1"); }
+}
