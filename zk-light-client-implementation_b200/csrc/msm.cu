@@ -156,7 +156,7 @@ __global__ void k_digits(const u64 *__restrict__ scalars, size_t n, u32 *__restr
         }
     }
 }
-__global__ void k_scan(const u32 *__restrict__ counts, u32 *__restrict__ offsets) {      // one block per window, 1024 threads x 64 buckets
+__global__ void __launch_bounds__(1024) k_scan(const u32 *__restrict__ counts, u32 *__restrict__ offsets) {      // one block per window, 1024 threads x 64 buckets
     __shared__ u32 part[1024];
     const u32 *c = counts + (size_t)blockIdx.x * NBUCKET; u32 *o = offsets + (size_t)blockIdx.x * NBUCKET;
     u32 base = threadIdx.x * 64, s = 0;
