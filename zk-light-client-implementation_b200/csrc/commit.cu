@@ -3,6 +3,18 @@
 #include "ctx.h"
 #include "poseidon.cuh"
 
+u8 *ctx_arena(b200_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->arena_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr; ctx->arena_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->arena, bytes));
+        ctx->arena_bytes = bytes;
+    }
+    return (u8 *)ctx->arena;
+}
+
+
 const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits) {
     auto key = std::make_pair(log_n, rate_bits);
     auto it = ctx->lde_scale.find(key);

@@ -38,6 +38,8 @@ struct PhaseTimer {     // RAII: records start/stop events for one named phase w
     ~PhaseTimer() { if (on) cudaEventRecord(ctx->timing_events[idx].second.second, ctx->stream); }
 };
 
+// grow-only device scratch owned by the context (one allocation reused by every prove / msm call)
+u8 *ctx_arena(b200_ctx *ctx, size_t bytes);
 // coset scaling table for the LDE, cached per size
 const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits);
 // PolynomialBatch::from_values on device buffers: values [cols][n] -> coeffs_br [cols][n], lde [cols][n<<rate], digests

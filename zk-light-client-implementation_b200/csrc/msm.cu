@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) k_buckets(const u64 *__restrict__ points,
     buckets[b] = acc;
 }
 // chunked running sums: thread (win, chunk) covers buckets [start, start + CH)
-constexpr u32 CH = 256, NCHUNK = NBUCKET / CH;
+constexpr u32 CH = 64, NCHUNK = NBUCKET / CH;
 __global__ void __launch_bounds__(64) k_window_chunks(const xyzz *__restrict__ buckets, xyzz *__restrict__ chunk_acc) {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= NWIN * NCHUNK) return;
@@ -216,12 +216,19 @@ __global__ void __launch_bounds__(64) k_window_chunks(const xyzz *__restrict__ b
     }
     chunk_acc[t] = acc;
 }
-__global__ void k_window_final(const xyzz *__restrict__ chunk_acc, xyzz *__restrict__ out) {   // one thread per window sums its chunks
-    u32 win = blockIdx.x * blockDim.x + threadIdx.x;
-    if (win >= NWIN) return;
+// one block of 256 threads per window: each thread sums NCHUNK/256 chunk results, then a shared-memory tree
+__global__ void __launch_bounds__(256) k_window_final(const xyzz *__restrict__ chunk_acc, xyzz *__restrict__ out) {
+    __shared__ xyzz sh[256];
+    const u32 win = blockIdx.x, t = threadIdx.x;
     xyzz s = pt_identity();
-    for (u32 c = 0; c < NCHUNK; c++) pt_add(s, chunk_acc[win * NCHUNK + c]);
-    out[win] = s;
+    for (u32 c = t; c < NCHUNK; c += 256) pt_add(s, chunk_acc[win * NCHUNK + c]);
+    sh[t] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)t < off) { xyzz a = sh[t]; pt_add(a, sh[t + off]); sh[t] = a; }
+        __syncthreads();
+    }
+    if (t == 0) out[win] = sh[0];
 }
 
 }  // namespace
@@ -234,15 +241,22 @@ extern "C" int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const ui
         cudaSetDevice(ctx->device);
         if (!d_points || !d_scalars || !out_affine || n == 0 || n > (size_t(1) << 28)) throw ApiErr{B200_ERR_BAD_ARG, "b200_msm_g1: bad arguments"};
         cudaStream_t st = ctx->stream;
-        DevBuf digits(n * NWIN * 4), counts((size_t)NWIN * NBUCKET * 4), offsets((size_t)NWIN * NBUCKET * 4), cursor((size_t)NWIN * NBUCKET * 4),
-            sorted(n * NWIN * 4), buckets((size_t)NWIN * NBUCKET * sizeof(xyzz)), chunks((size_t)NWIN * NCHUNK * sizeof(xyzz)), wins(NWIN * sizeof(xyzz));
+        // all scratch comes from the context arena (cudaMalloc/cudaFree per call cost more than the kernels at 2^18 points)
+        auto rnd = [](size_t b) { return (b + 255) & ~size_t(255); };
+        const size_t sz_digits = rnd(n * NWIN * 4), sz_cnt = rnd((size_t)NWIN * NBUCKET * 4), sz_sorted = rnd(n * NWIN * 4),
+                     sz_buckets = rnd((size_t)NWIN * NBUCKET * sizeof(xyzz)), sz_chunks = rnd((size_t)NWIN * NCHUNK * sizeof(xyzz)), sz_wins = rnd(NWIN * sizeof(xyzz));
+        u8 *base = ctx_arena(ctx, sz_digits + 3 * sz_cnt + sz_sorted + sz_buckets + sz_chunks + sz_wins);
+        struct Buf { void *p; size_t bytes; };
+        size_t off = 0; auto take = [&](size_t b) { Buf r{base + off, b}; off += b; return r; };
+        Buf digits = take(sz_digits), counts = take(sz_cnt), offsets = take(sz_cnt), cursor = take(sz_cnt), sorted = take(sz_sorted),
+            buckets = take(sz_buckets), chunks = take(sz_chunks), wins = take(sz_wins);
         CUDA_TRY(cudaMemsetAsync(counts.p, 0, counts.bytes, st)); CUDA_TRY(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
         k_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, (u32 *)digits.p, (u32 *)counts.p); LAUNCHED(1);
         k_scan<<<NWIN, 1024, 0, st>>>((const u32 *)counts.p, (u32 *)offsets.p); LAUNCHED(1);
         k_scatter<<<(unsigned)((n * NWIN + 255) / 256), 256, 0, st>>>((const u32 *)digits.p, n, (const u32 *)offsets.p, (u32 *)cursor.p, (u32 *)sorted.p); LAUNCHED(1);
         k_buckets<<<(unsigned)(((size_t)NWIN * NBUCKET + 127) / 128), 128, 0, st>>>(d_points, n, (const u32 *)counts.p, (const u32 *)offsets.p, (const u32 *)sorted.p, (xyzz *)buckets.p); LAUNCHED(1);
         k_window_chunks<<<(NWIN * NCHUNK + 63) / 64, 64, 0, st>>>((const xyzz *)buckets.p, (xyzz *)chunks.p); LAUNCHED(1);
-        k_window_final<<<1, 32, 0, st>>>((const xyzz *)chunks.p, (xyzz *)wins.p); LAUNCHED(1);
+        k_window_final<<<NWIN, 256, 0, st>>>((const xyzz *)chunks.p, (xyzz *)wins.p); LAUNCHED(1);
         std::vector<xyzz> w(NWIN);
         CUDA_TRY(cudaMemcpyAsync(w.data(), wins.p, NWIN * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));

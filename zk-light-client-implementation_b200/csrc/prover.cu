@@ -40,7 +40,6 @@ struct Arena {      // bump allocator over one device allocation, reset per prov
     u8 *base = nullptr; size_t cap = 0, off = 0;
     u64 *take(size_t n_u64) { size_t b = (n_u64 * 8 + 255) & ~size_t(255); if (off + b > cap) throw ApiErr{B200_ERR_OOM, "arena exhausted"}; u64 *p = (u64 *)(base + off); off += b; return p; }
 };
-static u8 *ctx_arena(b200_ctx *ctx, size_t bytes);   // defined below (grow-only scratch owned by the context)
 
 // Small host<->device transfers go through one pinned staging buffer per context: copies to/from pageable memory are
 // synchronous and staged by the driver (tens of microseconds each, ~15 per proof), which matters for the small
@@ -414,17 +413,6 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     memcpy(buf, out.data(), out.size());
     *proof_out = buf; *proof_len = out.size();
     return B200_OK;
-}
-
-static u8 *ctx_arena(b200_ctx *ctx, size_t bytes) {
-    if (bytes > ctx->arena_bytes) {
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (ctx->arena) cudaFree(ctx->arena);
-        ctx->arena = nullptr; ctx->arena_bytes = 0;
-        CUDA_TRY(cudaMalloc(&ctx->arena, bytes));
-        ctx->arena_bytes = bytes;
-    }
-    return (u8 *)ctx->arena;
 }
 
 int ctx_fail(b200_ctx *ctx, int code, const std::string &msg);
