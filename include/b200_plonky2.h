@@ -80,6 +80,12 @@ int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
 int b200_ctx_synchronize(b200_ctx *ctx);
 const char *b200_last_error(const b200_ctx *ctx);      /* valid until the next call on ctx */
 void b200_free(void *p);                                /* frees buffers returned by the library */
+/* Page-locked host memory for witness buffers handed to b200_prove / b200_lde_commit: a copy from pageable memory is
+ * staged synchronously by the driver (~1 ms of host time for the 8.8 MB witness of a recursion proof), a copy from
+ * these buffers overlaps the first kernels.  Replaces the Vec allocation of PartitionWitness::full_witness()
+ * (plonky2 @ 2244a9d, iop/witness.rs) in the patched prove(); ordinary malloc'd buffers stay valid inputs. */
+int b200_host_alloc(b200_ctx *ctx, size_t bytes, void **out);
+void b200_host_free(void *p);
 /* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t b200_kernel_launches(const b200_ctx *ctx);
 /* Phase timing: when enabled, CUDA events are recorded on the context stream around the prover's phases

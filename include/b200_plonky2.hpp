@@ -27,6 +27,8 @@ public:
     Context(const Context &) = delete; Context &operator=(const Context &) = delete;
     b200_ctx *raw() const { return ctx_; }
     void check(int rc) const { if (rc) throw Error(rc, b200_last_error(ctx_)); }
+    // page-locked witness buffer (b200_host_alloc); release with b200_host_free
+    uint64_t *alloc_witness(size_t num_wires, size_t degree) const { void *p = nullptr; check(b200_host_alloc(ctx_, num_wires * degree * 8, &p)); return (uint64_t *)p; }
 private:
     b200_ctx *ctx_ = nullptr;
 };

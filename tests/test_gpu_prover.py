@@ -99,3 +99,18 @@ def test_bad_arguments(ctx):
     out = ctypes.POINTER(ctypes.c_uint8)(); ln = ctypes.c_size_t()
     assert lib.b200_prove(ctx.h, None, None, None, 0, ctypes.c_uint64(0), ctypes.byref(out), ctypes.byref(ln)) == -1
     assert b"null" in lib.b200_last_error(ctx.h)
+
+
+@pytest.mark.gpu
+def test_pinned_witness_buffer_gives_same_proof():
+    """b200_host_alloc'd witness buffers are an optimisation only: same bytes as with a pageable buffer."""
+    import b200_plonky2 as bp
+    from b200_plonky2 import workloads
+    ctx = bp.Context(0)
+    cd = workloads.build("rec", 8, seed=11); cd.upload(ctx)
+    a = cd.prove(ctx)
+    w = ctx.pinned_copy(cd.wires)
+    assert w.ctypes.data != cd.wires.ctypes.data and (w == cd.wires).all()
+    b = cd.prove(ctx, wires=w)
+    assert a == b
+    cd.free()

@@ -8,12 +8,14 @@ from b200_plonky2 import workloads
 kind = sys.argv[1]; db = int(sys.argv[2]); hs = sys.argv[3] if len(sys.argv) > 3 else "gl"
 ctx = bp.Context(0)
 cd = workloads.build(kind, db, seed=3, hasher=hs); cd.upload(ctx)
-for _ in range(3): cd.prove(ctx)
+w = ctx.pinned_copy(cd.wires) if os.environ.get('PAGEABLE') != '1' else cd.wires
+for _ in range(3): cd.prove(ctx, wires=w)
 ctx.enable_timing(True); ctx.timings()
 l0 = ctx.kernel_launches(); t0 = time.time()
 N = 10
-for _ in range(N): cd.prove(ctx)
+for _ in range(N): cd.prove(ctx, wires=w)
 wall = (time.time() - t0) / N * 1e3
 ph = ctx.timings()
 print(json.dumps({"shape": f"{kind} 2^{db} {hs}", "wall_ms_per_proof": round(wall, 3), "launches_per_proof": (ctx.kernel_launches() - l0) / N,
-                  "phases_ms": {k: round(v[0] / N, 4) for k, v in ph.items()}, "sum_phases_ms": round(sum(v[0] for v in ph.values()) / N, 3)}))
+                  "phases_ms": {k: round(v[0] / N, 4) for k, v in ph.items()}, "sum_phases_ms": round(sum(v[0] for k, v in ph.items() if not k.startswith("_")) / N, 3),
+                  "host_busy_ms": round((ph["_host_total"][0] - ph["_host_sync_wait"][0]) / N, 3) if "_host_total" in ph else None}))

@@ -48,6 +48,8 @@ _sig("b200_ctx_synchronize", c_int, c_void_p)
 _sig("b200_last_error", ctypes.c_char_p, c_void_p)
 _sig("b200_free", None, c_void_p)
 _sig("b200_kernel_launches", c_u64, c_void_p)
+_sig("b200_host_alloc", c_int, c_void_p, c_size_t, c_void_p)
+_sig("b200_host_free", None, c_void_p)
 _sig("b200_merkle_num_u64", c_size_t, c_u32, c_u32)
 _sig("b200_ctx_enable_timing", c_int, c_void_p, c_int)
 _sig("b200_ctx_timings", ctypes.c_char_p, c_void_p)
@@ -65,7 +67,7 @@ _sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
 _sig("b200_verify_error", ctypes.c_char_p)
 
 EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_synchronize", "b200_last_error",
-           "b200_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
+           "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
            "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
            "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
            "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev"]
@@ -97,6 +99,18 @@ class Context:
         self._chk(lib.b200_ctx_synchronize(self.h))
     def kernel_launches(self):
         return int(lib.b200_kernel_launches(self.h))
+    def pinned_empty(self, shape, dtype=np.uint64):
+        """numpy array over page-locked memory from b200_host_alloc (freed when the array and its views are collected)."""
+        import weakref
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = c_void_p()
+        self._chk(lib.b200_host_alloc(self.h, nbytes, ctypes.byref(p)))
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        weakref.finalize(buf, lib.b200_host_free, c_void_p(p.value))
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    def pinned_copy(self, a):
+        out = self.pinned_empty(a.shape, a.dtype); out[...] = a
+        return out
     def enable_timing(self, on=True):
         self._chk(lib.b200_ctx_enable_timing(self.h, int(on)))
     def timings(self):

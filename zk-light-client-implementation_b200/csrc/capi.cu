@@ -68,6 +68,15 @@ int b200_ctx_synchronize(b200_ctx *ctx) {
 
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void b200_free(void *p) { free(p); }
+int b200_host_alloc(b200_ctx *ctx, size_t bytes, void **out) {
+    API_BEGIN(ctx)
+    if (!out) throw ApiErr{B200_ERR_BAD_ARG, "b200_host_alloc: null out"};
+    *out = nullptr;
+    if (cudaMallocHost(out, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); throw ApiErr{B200_ERR_OOM, "b200_host_alloc: cudaMallocHost failed"}; }
+    return B200_OK;
+    API_END(ctx)
+}
+void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 uint64_t b200_kernel_launches(const b200_ctx *) { return g_b200_launches.load(); }
 
 int b200_ctx_enable_timing(b200_ctx *ctx, int enable) {
@@ -95,6 +104,14 @@ const char *b200_ctx_timings(b200_ctx *ctx) {
     for (size_t i = 0; i < order.size(); i++) {
         char buf[160]; snprintf(buf, sizeof buf, "%s\"%s\": [%.4f, %d]", i ? ", " : "", order[i].c_str(), acc[order[i]].first, acc[order[i]].second);
         j += buf;
+    }
+    if (ctx->host_proofs) {
+        char buf[200]; snprintf(buf, sizeof buf, "%s\"_host_total\": [%.4f, %d], \"_host_sync_wait\": [%.4f, %d]", order.empty() ? "" : ", ",
+                                ctx->host_total_ms, ctx->host_proofs, ctx->host_wait_ms, ctx->host_syncs);
+        j += buf;
+        for (size_t i = 0; i < ctx->host_seg_ms.size(); i++) { snprintf(buf, sizeof buf, ", \"_host_before_sync_%02zu\": [%.4f, %d]", i, ctx->host_seg_ms[i], ctx->host_proofs); j += buf; }
+        ctx->host_seg_ms.clear();
+        ctx->host_total_ms = ctx->host_wait_ms = 0; ctx->host_proofs = ctx->host_syncs = 0;
     }
     j += "}";
     ctx->timing_json = j;

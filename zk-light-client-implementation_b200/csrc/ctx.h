@@ -7,6 +7,7 @@
 #include <new>
 #include <memory>
 #include <vector>
+#include <chrono>
 
 struct ApiErr { int code; std::string msg; };
 
@@ -25,6 +26,8 @@ struct b200_ctx {
     bool timing = false;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timing_events;
     std::string timing_json;
+    double host_total_ms = 0, host_wait_ms = 0; int host_proofs = 0, host_syncs = 0;   // wall clock of prove() and of its stream syncs
+    std::vector<double> host_seg_ms; size_t host_seg_i = 0; std::chrono::steady_clock::time_point host_seg_t0;   // host-busy time before the i-th sync of a proof
 };
 struct PhaseTimer {     // RAII: records start/stop events for one named phase when timing is enabled
     b200_ctx *ctx; size_t idx; bool on;

@@ -76,6 +76,91 @@ __global__ void __launch_bounds__(MK_THREADS) k_merkle_level(const u64 *__restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Latency-oriented variant for the small launches (upper Merkle levels of every tree, FRI layer trees of small
+// proofs): FOUR lanes cooperate on one permutation -- lane q holds state words 3q..3q+2, the S-box layer runs 3-wide per
+// lane, the MDS layer gathers the 12 words with quad shuffles and each lane produces its 3 outputs.  A thread-per-
+// permutation kernel needs ~40 us per tree level when the level cannot fill the machine (one warp walks 32.6 k
+// dependent-ish instructions); the quad version cuts the per-level latency several times.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quad_mds(u64 s[3], int q, int quad_base) {
+    const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    // gather the state already rotated by 3q words, so that every lane runs the same (divergence-free) dot products:
+    // rot[j] = state[(j + 3q) % 12]
+    u32 lo[12], hi[12];
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const int src = quad_base + ((q + d) & 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[3 * d + k] = __shfl_sync(0xffffffffu, (u32)s[k], src);
+            hi[3 * d + k] = __shfl_sync(0xffffffffu, (u32)(s[k] >> 32), src);
+        }
+    }
+    const u32 diag = q == 0 ? 8u : 0u;                  // MDS diagonal: only out[0] += 8 * state[0]
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        u64 al = 0, ah = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { al += (u64)lo[(i + k) % 12] * C[i]; ah += (u64)hi[(i + k) % 12] * C[i]; }
+        if (k == 0) { al += (u64)lo[0] * diag; ah += (u64)hi[0] * diag; }
+        s[k] = poseidon_reduce96(al, ah);
+    }
+}
+// state words of this lane in s[3]; all 32 lanes of the warp must call (quads may hold dummy states)
+__device__ __noinline__ void poseidon_permute_quad(u64 s[3], int q, int quad_base) {
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        const u64 *rc = d_POSEIDON_RC + 12 * r + 3 * q;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            u64 c = rc[k];
+            u64 x = s[k] + c;
+            if (x < c) x += GL_EPS;
+            if (full || (q == 0 && k == 0)) x = poseidon_sbox(x);
+            s[k] = x;
+        }
+        quad_mds(s, q, quad_base);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[k] = gl_canon(s[k]);
+}
+
+__global__ void __launch_bounds__(128) k_merkle_level_quad(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n_out) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t node = t >> 2; const int q = (int)(t & 3), quad_base = (int)(threadIdx.x & 31 & ~3);
+    const bool active = node < n_out;
+    if (!active) node = n_out - 1;
+    const u64 *p = in + 8 * node;
+    u64 s[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { int e = 3 * q + k; s[k] = e < 8 ? p[e] : 0; }
+    poseidon_permute_quad(s, q, quad_base);
+    if (active) {
+        if (q == 0) { out[4 * node] = s[0]; out[4 * node + 1] = s[1]; out[4 * node + 2] = s[2]; }
+        if (q == 1) out[4 * node + 3] = s[0];
+    }
+}
+// row-major leaves (FRI layers): width > 4 words, sponge with rate 8
+__global__ void __launch_bounds__(128) k_leaves_rowmajor_quad(const u64 *__restrict__ data, size_t width, size_t L, u64 *__restrict__ digests) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t leaf = t >> 2; const int q = (int)(t & 3), quad_base = (int)(threadIdx.x & 31 & ~3);
+    const bool active = leaf < L;
+    if (!active) leaf = L - 1;
+    const u64 *row = data + leaf * width;
+    u64 s[3] = {0, 0, 0};
+    for (size_t c = 0; c < width; c += 8) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { int e = 3 * q + k; if (e < 8 && c + e < width) s[k] = row[c + e]; }
+        poseidon_permute_quad(s, q, quad_base);
+    }
+    if (active) {
+        if (q == 0) { digests[4 * leaf] = s[0]; digests[4 * leaf + 1] = s[1]; digests[4 * leaf + 2] = s[2]; }
+        if (q == 1) digests[4 * leaf + 3] = s[0];
+    }
+}
+#define QUAD_MAX_NODES (size_t(148) * 16 * 32 / 4)      /* below ~19 k permutations a launch cannot fill the machine thread-per-permutation */
+
 void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digests, cudaStream_t st) {
     size_t L = size_t(1) << log_L;
     k_leaves_colmajor<<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, cols, L, digests);
@@ -83,7 +168,8 @@ void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digest
 }
 void merkle_leaves_rowmajor(const u64 *data, size_t width, int log_L, u64 *digests, cudaStream_t st) {
     size_t L = size_t(1) << log_L;
-    k_leaves_rowmajor<<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, width, L, digests);
+    if (width > 4 && L <= QUAD_MAX_NODES) k_leaves_rowmajor_quad<<<(unsigned)((4 * L + 127) / 128), 128, 0, st>>>(data, width, L, digests);
+    else k_leaves_rowmajor<<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, width, L, digests);
     LAUNCHED(1);
 }
 void merkle_build(u64 *digests, int log_L, int cap_height, cudaStream_t st) {
@@ -91,7 +177,8 @@ void merkle_build(u64 *digests, int log_L, int cap_height, cudaStream_t st) {
     for (int lv = log_L; lv > cap_height; lv--) {
         size_t n = size_t(1) << lv;
         u64 *nxt = cur + 4 * n;
-        k_merkle_level<<<(unsigned)((n / 2 + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(cur, nxt, n / 2);
+        if (n / 2 <= QUAD_MAX_NODES) k_merkle_level_quad<<<(unsigned)((4 * (n / 2) + 127) / 128), 128, 0, st>>>(cur, nxt, n / 2);
+        else k_merkle_level<<<(unsigned)((n / 2 + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(cur, nxt, n / 2);
         LAUNCHED(1);
         cur = nxt;
     }

@@ -63,7 +63,14 @@ struct Staging {
         CUDA_TRY(cudaMemcpyAsync(ddst, p, bytes, cudaMemcpyHostToDevice, st));
     }
     void sync() {
-        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ctx->timing) {
+            auto t0 = std::chrono::steady_clock::now();
+            if (ctx->host_seg_ms.size() <= ctx->host_seg_i) ctx->host_seg_ms.resize(ctx->host_seg_i + 1, 0.0);
+            ctx->host_seg_ms[ctx->host_seg_i++] += std::chrono::duration<double, std::milli>(t0 - ctx->host_seg_t0).count();
+            CUDA_TRY(cudaStreamSynchronize(st));
+            ctx->host_seg_t0 = std::chrono::steady_clock::now();
+            ctx->host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ctx->host_syncs++;
+        } else CUDA_TRY(cudaStreamSynchronize(st));
         for (auto &q : pending) memcpy(q.dst, q.src, q.bytes);
         pending.clear();
     }
@@ -102,6 +109,9 @@ static void dump_dev(const char *dir, const char *name, const void *d, size_t by
 static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in, bool wires_on_device, const u64 *pis, size_t n_pis,
                       u64 pow_hint, uint8_t **proof_out, size_t *proof_len) {
     cudaStream_t st = ctx->stream;
+    struct WallTimer { b200_ctx *c; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+                       ~WallTimer() { if (c->timing) { c->host_total_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); c->host_proofs++; } } } wall_timer{ctx};
+    ctx->host_seg_i = 0; ctx->host_seg_t0 = std::chrono::steady_clock::now();
     const int nlog = (int)k->degree_bits, rb = (int)k->rate_bits, chh = (int)k->cap_height;
     const int Llog = nlog + rb;
     const size_t n = size_t(1) << nlog, N = n << rb;
@@ -136,7 +146,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         // flight (the LDE takes longer than the PCIe copy, so the H2D time disappears behind it); hash once all columns are in
         u64 *t = A.take((size_t)W * n); d_wires = t;
         if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        const u32 nchunks = W >= 32 ? 6 : 1;
+        const u32 nchunks = W >= 32 ? (u32)std::min<size_t>(6, std::max<size_t>(1, ((size_t)W * n) >> 19)) : 1;   // >= 2^19 words per chunk: small proofs are launch-bound
         std::vector<cudaEvent_t> evs(nchunks);
         cudaEvent_t start_ev; CUDA_TRY(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(start_ev, st)); CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, start_ev, 0));   // arena reuse ordering
