@@ -157,6 +157,43 @@ def run_b200(args):
     ms_e2e = timed(False, args.steps, True)
     sampler.stop = True; sampler.join(timeout=2)
 
+    # ---- one whole BFT-finality block, measured (second half of BASELINE.json's metric; configs[1] at N=1, configs[2] at N=8):
+    # k signed approvals -> k sig-shaped sub-proofs sharded round-robin over the ranks (host witnesses through b200_prove),
+    # ONE all-gather of the digest records, then on rank 0 the sequential fold: (k + 55) recursive_proof-shaped proofs
+    # (2^13 rows, 135 wires) and the final PoseidonBN128 wrap (2^12 rows).  Wall clock between two barriers, max over ranks.
+    block = None
+    if not args.no_block:
+        try:
+            k = args.block_signatures
+            rec_cd = wrap_cd = None
+            if rank == 0:
+                rec_cd = workloads.build("rec", 13, seed=3); rec_cd.upload(ctx)
+                wrap_cd = workloads.build("rec", 12, seed=3, hasher="bn254"); wrap_cd.upload(ctx)
+                rec_w = ctx.pinned_copy(rec_cd.wires); wrap_w = ctx.pinned_copy(wrap_cd.wires)
+                rec_cd.prove(ctx, wires=rec_w); wrap_cd.prove(ctx, wires=wrap_w)
+            mine = sharding.shard_indices(k, world, rank)
+            barrier(); t0 = time.perf_counter()
+            recs = [sharding.digest_record(i, prove(False)) for i in mine]
+            t_sig = time.perf_counter() - t0
+            rows = sharding.gather_records(recs, dist, "cuda", (k + world - 1) // world)
+            assert len(rows) == k and [int(r[0]) for r in rows] == list(range(k))
+            t_gather = time.perf_counter() - t0
+            if rank == 0:
+                for _ in range(k + 55): rec_cd.prove(ctx, wires=rec_w)
+                wrap_cd.prove(ctx, wires=wrap_w)
+            barrier(); t_all = time.perf_counter() - t0
+            tt = torch.tensor([t_sig, t_gather, t_all], dtype=torch.float64, device="cuda")
+            if dist: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_sig, t_gather, t_all = (float(x) for x in tt.tolist())
+            block = {"bft_block_ms": round(t_all * 1e3, 1), "signature_stage_ms": round(t_sig * 1e3, 1),
+                     "digest_all_gather_ms": round((t_gather - t_sig) * 1e3, 2) if world > 1 else 0.0,
+                     "fold_and_wrap_ms": round((t_all - t_gather) * 1e3, 1), "signatures": k, "sig_proofs_per_rank_max": len(sharding.shard_indices(k, world, 0)),
+                     "recursive_proofs": k + 55, "note": "measured: k sig-shaped proofs sharded over the ranks (host witnesses), one all-gather, then the "
+                     "sequential fold of k+55 recursive_proof-shaped proofs + 1 BN128 wrap on rank 0; prover time only (witness generation and circuit builds stay in Rust)"}
+            if rank == 0: rec_cd.free(); wrap_cd.free()
+        except Exception as e:
+            block = {"bft_block_ms": None, "error": str(e)}
+
     total_proofs = args.steps * world
     value = total_proofs / (ms_dev * 1e-3)
     e2e_value = total_proofs / (ms_e2e * 1e-3)
@@ -192,6 +229,7 @@ def run_b200(args):
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
                 "phases_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in phases.items()},
                 "proof_bytes": proof_len[0]}
+    if block is not None: out_json["bft_finality_block"] = block
     if world == 1 and not args.no_aux:
         # the other proof shapes of one BFT-finality block (second half of BASELINE.json's metric): a recursive_proof-shaped
         # circuit (13 standard gates, 135 wires, 2^13 rows) and the final PoseidonBN128 wrap (2^12 rows), ms per proof
@@ -253,6 +291,8 @@ def main():
     ap.add_argument("--cpu-sample-log-n", type=int, default=14)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--no-block", action="store_true", help="skip the measured whole-block run (k sig proofs + fold + wrap)")
+    ap.add_argument("--block-signatures", type=int, default=73, help="signed approvals in the block (prove_random fixture: 73)")
     args = ap.parse_args()
     if args.impl == "reference": run_reference(args)
     else: run_b200(args)

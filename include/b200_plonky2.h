@@ -153,6 +153,11 @@ int b200_fri_fold(b200_ctx *ctx, const uint64_t *values, uint32_t log_len, uint3
  * scalars: n x 4 u64 canonical (< r).  out_affine: 8 u64 (all-zero = infinity). */
 int b200_msm_g1(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[8]);
 int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[8]);
+/* Same on G2 (the twist y^2 = x^3 + 3/(9+u) over F_q2 = F_q[u]/(u^2+1)): the B-query MSM of groth16.Prove.
+ * points: 16 u64 each = x.A0, x.A1, y.A0, y.A1 (gnark-crypto E2{A0, A1} order), 4 canonical limbs per coordinate;
+ * out_affine: 16 u64 in the same order. */
+int b200_msm_g2(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[16]);
+int b200_msm_g2_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[16]);
 /* Poseidon permutation of `count` independent 12-word states (self-test / throughput probe). */
 int b200_poseidon_permute(b200_ctx *ctx, uint64_t *states, size_t count);
 

@@ -71,3 +71,56 @@ def test_msm_linearity_at_scale(ctx):
     ra, rb, rab = ctx.msm_g1(P, A), ctx.msm_g1(P, B), ctx.msm_g1(P, AB)
     assert ec.add(ra, rb) == rab
     assert ra == ec.mul(sum(x * (int(i) + 1) for x, i in zip(a, idx)) % ec.R, ec.G)
+
+
+# ---------------------------------------------------------------- G2 ----------------------------------------------------------------
+def test_oracle_g2_generator():
+    assert ec.g2_on_curve(ec.G2) and ec.g2_mul(ec.R, ec.G2) is None
+    assert ec.g2_on_curve(ec.g2_mul(987654321, ec.G2))
+    assert ec.g2_add(ec.g2_mul(7, ec.G2), ec.g2_mul(ec.R - 7, ec.G2)) is None
+    # distributivity through the discrete log, which the GPU tests rely on
+    assert ec.g2_msm([ec.g2_mul(3, ec.G2), ec.g2_mul(5, ec.G2)], [11, 13]) == ec.g2_mul(3 * 11 + 5 * 13, ec.G2)
+
+def _g2_row(p): return _limbs(p[0][0]) + _limbs(p[0][1]) + _limbs(p[1][0]) + _limbs(p[1][1])
+
+def _rand_g2(n, seed, small=False):
+    rng = np.random.default_rng(seed)
+    ks = [int(x) for x in rng.integers(1, 1 << 62, size=n)]
+    pts = [ec.g2_mul(k, ec.G2) for k in ks]
+    if small: scal = [int(x) for x in rng.integers(0, 1 << 20, size=n)]
+    else: scal = [int.from_bytes(rng.bytes(32), "little") % ec.R for _ in range(n)]
+    P = np.array([_g2_row(p) for p in pts], dtype=np.uint64)
+    S = np.array([_limbs(s) for s in scal], dtype=np.uint64)
+    return pts, scal, ks, P, S
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,small", [(1, False), (5, False), (200, False), (200, True)])
+def test_msm_g2_matches_oracle(ctx, n, small):
+    pts, scal, ks, P, S = _rand_g2(n, 40 + n, small)
+    expect = ec.g2_mul(sum(s * k for s, k in zip(scal, ks)) % ec.R, ec.G2)
+    if n <= 5: assert ec.g2_msm(pts, scal) == expect
+    assert ctx.msm_g2(P, S) == expect
+
+@pytest.mark.gpu
+def test_msm_g2_edge_cases_and_linearity(ctx):
+    pts, scal, ks, P, S = _rand_g2(32, 6)
+    S0 = S.copy(); S0[:] = 0
+    assert ctx.msm_g2(P, S0) is None
+    P2 = P.copy(); P2[3] = 0
+    assert ctx.msm_g2(P2, S) == ec.g2_mul(sum(s * k for i, (s, k) in enumerate(zip(scal, ks)) if i != 3) % ec.R, ec.G2)
+    Pm = np.repeat(P[:1], 40, axis=0); Sm = np.repeat(S[:1], 40, axis=0)
+    assert ctx.msm_g2(Pm, Sm) == ec.g2_mul(40 * scal[0] * ks[0] % ec.R, ec.G2)
+    Sn = Sm.copy(); Sn[20:] = np.array(_limbs((ec.R - scal[0]) % ec.R), dtype=np.uint64)
+    assert ctx.msm_g2(Pm, Sn) is None
+    # 2^14 points drawn from 32 distinct ones: closed form through the discrete logs, and additivity in the scalars
+    n = 1 << 14
+    rng = np.random.default_rng(9)
+    idx = rng.integers(0, 32, size=n)
+    Pn = P[idx]
+    a = [int.from_bytes(rng.bytes(31), "little") for _ in range(n)]
+    b = [int.from_bytes(rng.bytes(31), "little") for _ in range(n)]
+    A = np.array([_limbs(x) for x in a], dtype=np.uint64); B = np.array([_limbs(x) for x in b], dtype=np.uint64)
+    AB = np.array([_limbs((x + y) % ec.R) for x, y in zip(a, b)], dtype=np.uint64)
+    ra, rb, rab = ctx.msm_g2(Pn, A), ctx.msm_g2(Pn, B), ctx.msm_g2(Pn, AB)
+    assert ec.g2_add(ra, rb) == rab
+    assert ra == ec.g2_mul(sum(x * ks[int(i)] for x, i in zip(a, idx)) % ec.R, ec.G2)

@@ -63,6 +63,8 @@ _sig("b200_poseidon_permute", c_int, c_void_p, c_void_p, c_size_t)
 _sig("b200_fri_fold", c_int, c_void_p, c_void_p, c_u32, c_u32, c_void_p, c_u64, c_void_p)
 _sig("b200_msm_g1", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
 _sig("b200_msm_g1_dev", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
+_sig("b200_msm_g2", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
+_sig("b200_msm_g2_dev", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
 _sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
 _sig("b200_verify_error", ctypes.c_char_p)
 
@@ -70,7 +72,7 @@ EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_c
            "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
            "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
            "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
-           "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev"]
+           "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev", "b200_msm_g2", "b200_msm_g2_dev"]
 
 def _np(a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
@@ -149,6 +151,13 @@ class Context:
         self._chk(lib.b200_msm_g1(self.h, pp, sp, p.shape[0], out.ctypes.data_as(c_void_p)))
         x = sum(int(out[i]) << (64 * i) for i in range(4)); y = sum(int(out[4 + i]) << (64 * i) for i in range(4))
         return None if x == 0 and y == 0 else (x, y)
+    def msm_g2(self, points, scalars):
+        """points [n][16] u64 (x.A0, x.A1, y.A0, y.A1 limbs), scalars [n][4] u64 -> ((x0, x1), (y0, y1)) or None for infinity."""
+        p, pp = _np(points); s, sp = _np(scalars)
+        out = np.zeros(16, dtype=np.uint64)
+        self._chk(lib.b200_msm_g2(self.h, pp, sp, p.shape[0], out.ctypes.data_as(c_void_p)))
+        v = [sum(int(out[4 * k + i]) << (64 * i) for i in range(4)) for k in range(4)]
+        return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
     def poseidon_permute(self, states):
         a, p = _np(np.array(states, dtype=np.uint64, copy=True))
         self._chk(lib.b200_poseidon_permute(self.h, p, a.shape[0]))

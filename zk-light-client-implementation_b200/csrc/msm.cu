@@ -87,55 +87,91 @@ static fq fq_inv_host(const fq &a) {      // Fermat, host only (final conversion
     return r;
 }
 
-struct xyzz { fq x, y, zz, zzz; };      // affine (x/zz, y/zzz); identity: zz == 0
-GL_HD xyzz pt_identity() { xyzz p; p.x = fq_zero(); p.y = fq_zero(); p.zz = fq_zero(); p.zzz = fq_zero(); return p; }
-GL_HD bool pt_is_identity(const xyzz &p) { return fq_is_zero(p.zz); }
+// F_q2 = F_q[u]/(u^2 + 1) for G2 (the twist y^2 = x^3 + 3/(9+u)); a = a0 + a1 u
+struct fq2 { fq a, b; };
+// one spelling of the field operations for both base fields, so the group law and the kernels are written once
+GL_HD fq f_add(const fq &x, const fq &y) { return fq_add(x, y); }
+GL_HD fq f_sub(const fq &x, const fq &y) { return fq_sub(x, y); }
+GL_HD fq f_mul(const fq &x, const fq &y) { return fq_mul(x, y); }
+GL_HD fq f_sqr(const fq &x) { return fq_mul(x, x); }
+GL_HD bool f_is_zero(const fq &x) { return fq_is_zero(x); }
+GL_HD void f_set_zero(fq &x) { x = fq_zero(); }
+GL_HD void f_set_one(fq &x) { x = fq_one(); }
+GL_HD fq2 f_add(const fq2 &x, const fq2 &y) { fq2 r; r.a = fq_add(x.a, y.a); r.b = fq_add(x.b, y.b); return r; }
+GL_HD fq2 f_sub(const fq2 &x, const fq2 &y) { fq2 r; r.a = fq_sub(x.a, y.a); r.b = fq_sub(x.b, y.b); return r; }
+GL_HD fq2 f_mul(const fq2 &x, const fq2 &y) {        // Karatsuba: 3 base multiplications
+    fq t0 = fq_mul(x.a, y.a), t1 = fq_mul(x.b, y.b), t2 = fq_mul(fq_add(x.a, x.b), fq_add(y.a, y.b));
+    fq2 r; r.a = fq_sub(t0, t1); r.b = fq_sub(fq_sub(t2, t0), t1); return r;
+}
+GL_HD fq2 f_sqr(const fq2 &x) {                       // (a+b)(a-b) + 2ab u
+    fq t = fq_mul(x.a, x.b);
+    fq2 r; r.a = fq_mul(fq_add(x.a, x.b), fq_sub(x.a, x.b)); r.b = fq_add(t, t); return r;
+}
+GL_HD bool f_is_zero(const fq2 &x) { return fq_is_zero(x.a) && fq_is_zero(x.b); }
+GL_HD void f_set_zero(fq2 &x) { x.a = fq_zero(); x.b = fq_zero(); }
+GL_HD void f_set_one(fq2 &x) { x.a = fq_one(); x.b = fq_zero(); }
+static fq f_inv_host(const fq &x) { return fq_inv_host(x); }
+static fq2 f_inv_host(const fq2 &x) {
+    fq d = fq_inv_host(fq_add(fq_mul(x.a, x.a), fq_mul(x.b, x.b)));
+    fq2 r; r.a = fq_mul(x.a, d); r.b = fq_sub(fq_zero(), fq_mul(x.b, d)); return r;
+}
+// affine coordinates <-> canonical little-endian limbs (4 per F_q element; F_q2 as a0 then a1, gnark-crypto's E2{A0, A1})
+GL_HD void f_load(fq &x, const u64 *p) { x = fq_to_mont(p); }
+GL_HD void f_load(fq2 &x, const u64 *p) { x.a = fq_to_mont(p); x.b = fq_to_mont(p + 4); }
+GL_HD void f_store(const fq &x, u64 *p) { fq_from_mont(x, p); }
+GL_HD void f_store(const fq2 &x, u64 *p) { fq_from_mont(x.a, p); fq_from_mont(x.b, p + 4); }
+template <class F> struct limbs_of { static constexpr int N = sizeof(F) / 8; };
 
-FQ_FN xyzz pt_double_affine(const fq &x, const fq &y) {     // dbl-2008-s-1 with ZZ = ZZZ = 1, a = 0
-    fq u = fq_add(y, y), v = fq_mul(u, u), w = fq_mul(u, v), s = fq_mul(x, v);
-    fq xx = fq_mul(x, x), m = fq_add(fq_add(xx, xx), xx);
-    xyzz r;
-    r.x = fq_sub(fq_mul(m, m), fq_add(s, s));
-    r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, y));
+template <class F> struct xyzz_t { F x, y, zz, zzz; };      // affine (x/zz, y/zzz); identity: zz == 0
+template <class F> GL_HD xyzz_t<F> pt_identity() { xyzz_t<F> p; f_set_zero(p.x); f_set_zero(p.y); f_set_zero(p.zz); f_set_zero(p.zzz); return p; }
+template <class F> GL_HD bool pt_is_identity(const xyzz_t<F> &p) { return f_is_zero(p.zz); }
+#define PT_FN template <class F> static __host__ __device__ __noinline__
+
+PT_FN xyzz_t<F> pt_double_affine(const F &x, const F &y) {     // dbl-2008-s-1 with ZZ = ZZZ = 1, a = 0
+    F u = f_add(y, y), v = f_sqr(u), w = f_mul(u, v), s = f_mul(x, v);
+    F xx = f_sqr(x), m = f_add(f_add(xx, xx), xx);
+    xyzz_t<F> r;
+    r.x = f_sub(f_sqr(m), f_add(s, s));
+    r.y = f_sub(f_mul(m, f_sub(s, r.x)), f_mul(w, y));
     r.zz = v; r.zzz = w;
     return r;
 }
-FQ_FN xyzz pt_double(const xyzz &p) {
+PT_FN xyzz_t<F> pt_double(const xyzz_t<F> &p) {
     if (pt_is_identity(p)) return p;
-    fq u = fq_add(p.y, p.y), v = fq_mul(u, u), w = fq_mul(u, v), s = fq_mul(p.x, v);
-    fq xx = fq_mul(p.x, p.x), m = fq_add(fq_add(xx, xx), xx);
-    xyzz r;
-    r.x = fq_sub(fq_mul(m, m), fq_add(s, s));
-    r.y = fq_sub(fq_mul(m, fq_sub(s, r.x)), fq_mul(w, p.y));
-    r.zz = fq_mul(v, p.zz); r.zzz = fq_mul(w, p.zzz);
+    F u = f_add(p.y, p.y), v = f_sqr(u), w = f_mul(u, v), s = f_mul(p.x, v);
+    F xx = f_sqr(p.x), m = f_add(f_add(xx, xx), xx);
+    xyzz_t<F> r;
+    r.x = f_sub(f_sqr(m), f_add(s, s));
+    r.y = f_sub(f_mul(m, f_sub(s, r.x)), f_mul(w, p.y));
+    r.zz = f_mul(v, p.zz); r.zzz = f_mul(w, p.zzz);
     return r;
 }
-FQ_FN void pt_madd(xyzz &a, const fq &x2, const fq &y2) {   // a += (x2, y2) affine (madd-2008-s)
-    if (pt_is_identity(a)) { a.x = x2; a.y = y2; a.zz = fq_one(); a.zzz = fq_one(); return; }
-    fq u2 = fq_mul(x2, a.zz), s2 = fq_mul(y2, a.zzz);
-    fq p = fq_sub(u2, a.x), r = fq_sub(s2, a.y);
-    if (fq_is_zero(p)) {
-        if (fq_is_zero(r)) a = pt_double_affine(x2, y2); else a = pt_identity();
+PT_FN void pt_madd(xyzz_t<F> &a, const F &x2, const F &y2) {   // a += (x2, y2) affine (madd-2008-s)
+    if (pt_is_identity(a)) { a.x = x2; a.y = y2; f_set_one(a.zz); f_set_one(a.zzz); return; }
+    F u2 = f_mul(x2, a.zz), s2 = f_mul(y2, a.zzz);
+    F p = f_sub(u2, a.x), r = f_sub(s2, a.y);
+    if (f_is_zero(p)) {
+        if (f_is_zero(r)) a = pt_double_affine(x2, y2); else a = pt_identity<F>();
         return;
     }
-    fq pp = fq_mul(p, p), ppp = fq_mul(p, pp), q = fq_mul(a.x, pp);
-    fq x3 = fq_sub(fq_sub(fq_mul(r, r), ppp), fq_add(q, q));
-    fq y3 = fq_sub(fq_mul(r, fq_sub(q, x3)), fq_mul(a.y, ppp));
-    a.x = x3; a.y = y3; a.zz = fq_mul(a.zz, pp); a.zzz = fq_mul(a.zzz, ppp);
+    F pp = f_sqr(p), ppp = f_mul(p, pp), q = f_mul(a.x, pp);
+    F x3 = f_sub(f_sub(f_sqr(r), ppp), f_add(q, q));
+    F y3 = f_sub(f_mul(r, f_sub(q, x3)), f_mul(a.y, ppp));
+    a.x = x3; a.y = y3; a.zz = f_mul(a.zz, pp); a.zzz = f_mul(a.zzz, ppp);
 }
-FQ_FN void pt_add(xyzz &a, const xyzz &b) {                 // a += b (add-2008-s)
+PT_FN void pt_add(xyzz_t<F> &a, const xyzz_t<F> &b) {          // a += b (add-2008-s)
     if (pt_is_identity(b)) return;
     if (pt_is_identity(a)) { a = b; return; }
-    fq u1 = fq_mul(a.x, b.zz), u2 = fq_mul(b.x, a.zz), s1 = fq_mul(a.y, b.zzz), s2 = fq_mul(b.y, a.zzz);
-    fq p = fq_sub(u2, u1), r = fq_sub(s2, s1);
-    if (fq_is_zero(p)) {
-        if (fq_is_zero(r)) a = pt_double(a); else a = pt_identity();
+    F u1 = f_mul(a.x, b.zz), u2 = f_mul(b.x, a.zz), s1 = f_mul(a.y, b.zzz), s2 = f_mul(b.y, a.zzz);
+    F p = f_sub(u2, u1), r = f_sub(s2, s1);
+    if (f_is_zero(p)) {
+        if (f_is_zero(r)) a = pt_double(a); else a = pt_identity<F>();
         return;
     }
-    fq pp = fq_mul(p, p), ppp = fq_mul(p, pp), q = fq_mul(u1, pp);
-    fq x3 = fq_sub(fq_sub(fq_mul(r, r), ppp), fq_add(q, q));
-    fq y3 = fq_sub(fq_mul(r, fq_sub(q, x3)), fq_mul(s1, ppp));
-    a.x = x3; a.y = y3; a.zz = fq_mul(fq_mul(a.zz, b.zz), pp); a.zzz = fq_mul(fq_mul(a.zzz, b.zzz), ppp);
+    F pp = f_sqr(p), ppp = f_mul(p, pp), q = f_mul(u1, pp);
+    F x3 = f_sub(f_sub(f_sqr(r), ppp), f_add(q, q));
+    F y3 = f_sub(f_mul(r, f_sub(q, x3)), f_mul(s1, ppp));
+    a.x = x3; a.y = y3; a.zz = f_mul(f_mul(a.zz, b.zz), pp); a.zzz = f_mul(f_mul(a.zzz, b.zzz), ppp);
 }
 
 constexpr int WBITS = 16, NWIN = 16;            // 16 x 16 = 256 >= 254 scalar bits
@@ -176,30 +212,37 @@ __global__ void k_scatter(const u32 *__restrict__ digits, size_t n, const u32 *_
     u32 pos = atomicAdd(&cursor[win * NBUCKET + d], 1u);
     sorted[win * n + offsets[win * NBUCKET + d] + pos] = (u32)i;
 }
+template <class F>
 __global__ void __launch_bounds__(128) k_buckets(const u64 *__restrict__ points, size_t n, const u32 *__restrict__ counts, const u32 *__restrict__ offsets,
-                                                 const u32 *__restrict__ sorted, xyzz *__restrict__ buckets) {
+                                                 const u32 *__restrict__ sorted, xyzz_t<F> *__restrict__ buckets) {
+    constexpr int NL = limbs_of<F>::N;
     size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (b >= (size_t)NWIN * NBUCKET) return;
     size_t win = b / NBUCKET;
-    xyzz acc = pt_identity();
+    xyzz_t<F> acc = pt_identity<F>();
     u32 cnt = counts[b], off = offsets[b];
     const u32 *idx = sorted + win * n + off;
     for (u32 k = 0; k < cnt; k++) {
-        const u64 *p = points + 8 * (size_t)idx[k];
-        u64 xl[4] = {p[0], p[1], p[2], p[3]}, yl[4] = {p[4], p[5], p[6], p[7]};
-        if ((xl[0] | xl[1] | xl[2] | xl[3] | yl[0] | yl[1] | yl[2] | yl[3]) == 0) continue;     // point at infinity
-        pt_madd(acc, fq_to_mont(xl), fq_to_mont(yl));
+        const u64 *p = points + 2 * NL * (size_t)idx[k];
+        u64 l[2 * NL], any = 0;
+#pragma unroll
+        for (int i = 0; i < 2 * NL; i++) { l[i] = p[i]; any |= l[i]; }
+        if (any == 0) continue;                                                                 // point at infinity
+        F x, y; f_load(x, l); f_load(y, l + NL);
+        pt_madd(acc, x, y);
     }
     buckets[b] = acc;
 }
 // chunked running sums: thread (win, chunk) covers buckets [start, start + CH)
 constexpr u32 CH = 64, NCHUNK = NBUCKET / CH;
-__global__ void __launch_bounds__(64) k_window_chunks(const xyzz *__restrict__ buckets, xyzz *__restrict__ chunk_acc) {
+template <class F>
+__global__ void __launch_bounds__(64) k_window_chunks(const xyzz_t<F> *__restrict__ buckets, xyzz_t<F> *__restrict__ chunk_acc) {
+    typedef xyzz_t<F> xyzz;
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= NWIN * NCHUNK) return;
     u32 win = t / NCHUNK, ch = t % NCHUNK, start = ch * CH;
     const xyzz *B = buckets + (size_t)win * NBUCKET;
-    xyzz run = pt_identity(), acc = pt_identity();
+    xyzz run = pt_identity<F>(), acc = pt_identity<F>();
     for (int d = (int)(start + CH - 1); d >= (int)start; d--) {
         if (d != 0) pt_add(run, B[d]);
         pt_add(acc, run);
@@ -207,24 +250,26 @@ __global__ void __launch_bounds__(64) k_window_chunks(const xyzz *__restrict__ b
     // acc = sum_d (d - start + 1) B_d ; wanted sum_d d B_d = acc + (start - 1) * run
     if (start > 0) {
         u32 k = start - 1;
-        xyzz kr = pt_identity(), base = run;
+        xyzz kr = pt_identity<F>(), base = run;
         while (k) { if (k & 1) pt_add(kr, base); base = pt_double(base); k >>= 1; }
         pt_add(acc, kr);
     } else {
-        xyzz neg = run; neg.y = fq_sub(fq_zero(), run.y);
+        xyzz neg = run; F z; f_set_zero(z); neg.y = f_sub(z, run.y);
         pt_add(acc, neg);
     }
     chunk_acc[t] = acc;
 }
 // one block of 256 threads per window: each thread sums NCHUNK/256 chunk results, then a shared-memory tree
-__global__ void __launch_bounds__(256) k_window_final(const xyzz *__restrict__ chunk_acc, xyzz *__restrict__ out) {
-    __shared__ xyzz sh[256];
+template <class F>
+__global__ void __launch_bounds__(128) k_window_final(const xyzz_t<F> *__restrict__ chunk_acc, xyzz_t<F> *__restrict__ out) {
+    typedef xyzz_t<F> xyzz;
+    __shared__ xyzz sh[128];                            // 16 KB (G1) / 32 KB (G2)
     const u32 win = blockIdx.x, t = threadIdx.x;
-    xyzz s = pt_identity();
-    for (u32 c = t; c < NCHUNK; c += 256) pt_add(s, chunk_acc[win * NCHUNK + c]);
+    xyzz s = pt_identity<F>();
+    for (u32 c = t; c < NCHUNK; c += 128) pt_add(s, chunk_acc[win * NCHUNK + c]);
     sh[t] = s;
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
+    for (int off = 64; off > 0; off >>= 1) {
         if ((int)t < off) { xyzz a = sh[t]; pt_add(a, sh[t + off]); sh[t] = a; }
         __syncthreads();
     }
@@ -235,11 +280,15 @@ __global__ void __launch_bounds__(256) k_window_final(const xyzz *__restrict__ c
 
 int ctx_fail(b200_ctx *ctx, int code, const std::string &msg);
 
-extern "C" int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[8]) {
+namespace {
+template <class F>
+static int msm_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t *out_affine, const char *who) {
+    typedef xyzz_t<F> xyzz;
+    constexpr int NL = limbs_of<F>::N;
     if (!ctx) return B200_ERR_BAD_ARG;
     try {
         cudaSetDevice(ctx->device);
-        if (!d_points || !d_scalars || !out_affine || n == 0 || n > (size_t(1) << 28)) throw ApiErr{B200_ERR_BAD_ARG, "b200_msm_g1: bad arguments"};
+        if (!d_points || !d_scalars || !out_affine || n == 0 || n > (size_t(1) << 28)) throw ApiErr{B200_ERR_BAD_ARG, std::string(who) + ": bad arguments"};
         cudaStream_t st = ctx->stream;
         // all scratch comes from the context arena (cudaMalloc/cudaFree per call cost more than the kernels at 2^18 points)
         auto rnd = [](size_t b) { return (b + 255) & ~size_t(255); };
@@ -251,37 +300,55 @@ extern "C" int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const ui
         Buf digits = take(sz_digits), counts = take(sz_cnt), offsets = take(sz_cnt), cursor = take(sz_cnt), sorted = take(sz_sorted),
             buckets = take(sz_buckets), chunks = take(sz_chunks), wins = take(sz_wins);
         CUDA_TRY(cudaMemsetAsync(counts.p, 0, counts.bytes, st)); CUDA_TRY(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
-        k_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, (u32 *)digits.p, (u32 *)counts.p); LAUNCHED(1);
-        k_scan<<<NWIN, 1024, 0, st>>>((const u32 *)counts.p, (u32 *)offsets.p); LAUNCHED(1);
-        k_scatter<<<(unsigned)((n * NWIN + 255) / 256), 256, 0, st>>>((const u32 *)digits.p, n, (const u32 *)offsets.p, (u32 *)cursor.p, (u32 *)sorted.p); LAUNCHED(1);
-        k_buckets<<<(unsigned)(((size_t)NWIN * NBUCKET + 127) / 128), 128, 0, st>>>(d_points, n, (const u32 *)counts.p, (const u32 *)offsets.p, (const u32 *)sorted.p, (xyzz *)buckets.p); LAUNCHED(1);
-        k_window_chunks<<<(NWIN * NCHUNK + 63) / 64, 64, 0, st>>>((const xyzz *)buckets.p, (xyzz *)chunks.p); LAUNCHED(1);
-        k_window_final<<<NWIN, 256, 0, st>>>((const xyzz *)chunks.p, (xyzz *)wins.p); LAUNCHED(1);
+        { PhaseTimer t(ctx, "msm_digits"); k_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, (u32 *)digits.p, (u32 *)counts.p); LAUNCHED(1); }
+        { PhaseTimer t(ctx, "msm_sort");
+          k_scan<<<NWIN, 1024, 0, st>>>((const u32 *)counts.p, (u32 *)offsets.p); LAUNCHED(1);
+          k_scatter<<<(unsigned)((n * NWIN + 255) / 256), 256, 0, st>>>((const u32 *)digits.p, n, (const u32 *)offsets.p, (u32 *)cursor.p, (u32 *)sorted.p); LAUNCHED(1); }
+        { PhaseTimer t(ctx, "msm_buckets"); k_buckets<F><<<(unsigned)(((size_t)NWIN * NBUCKET + 127) / 128), 128, 0, st>>>(d_points, n, (const u32 *)counts.p, (const u32 *)offsets.p, (const u32 *)sorted.p, (xyzz *)buckets.p); LAUNCHED(1); }
+        { PhaseTimer t(ctx, "msm_windows");
+          k_window_chunks<F><<<(NWIN * NCHUNK + 63) / 64, 64, 0, st>>>((const xyzz *)buckets.p, (xyzz *)chunks.p); LAUNCHED(1);
+          k_window_final<F><<<NWIN, 128, 0, st>>>((const xyzz *)chunks.p, (xyzz *)wins.p); LAUNCHED(1); }
         std::vector<xyzz> w(NWIN);
         CUDA_TRY(cudaMemcpyAsync(w.data(), wins.p, NWIN * sizeof(xyzz), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        xyzz acc = pt_identity();                      // Horner over the windows on the host: sum_w 2^(16 w) S_w
+        xyzz acc = pt_identity<F>();                   // Horner over the windows on the host: sum_w 2^(16 w) S_w
         for (int wi = NWIN - 1; wi >= 0; wi--) {
             for (int k = 0; k < WBITS; k++) acc = pt_double(acc);
             pt_add(acc, w[wi]);
         }
-        if (pt_is_identity(acc)) { for (int i = 0; i < 8; i++) out_affine[i] = 0; return B200_OK; }
-        fq zi2 = fq_inv_host(acc.zz), zi3 = fq_inv_host(acc.zzz);
-        fq_from_mont(fq_mul(acc.x, zi2), out_affine); fq_from_mont(fq_mul(acc.y, zi3), out_affine + 4);
+        if (pt_is_identity(acc)) { for (int i = 0; i < 2 * NL; i++) out_affine[i] = 0; return B200_OK; }
+        F zi2 = f_inv_host(acc.zz), zi3 = f_inv_host(acc.zzz);
+        f_store(f_mul(acc.x, zi2), out_affine); f_store(f_mul(acc.y, zi3), out_affine + NL);
         return B200_OK;
     } catch (const CudaErr &e) {
         char buf[256]; snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)e.e, cudaGetErrorString(e.e), e.file, e.line);
         cudaGetLastError(); return ctx_fail(ctx, e.e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA, buf);
     } catch (const ApiErr &e) { return ctx_fail(ctx, e.code, e.msg); }
 }
-
-extern "C" int b200_msm_g1(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[8]) {
+template <class F>
+static int msm_host(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t *out_affine, const char *who) {
     if (!ctx || !points || !scalars || !n) return B200_ERR_BAD_ARG;
     try {
         cudaSetDevice(ctx->device);
-        DevBuf p(n * 64), s(n * 32);
-        CUDA_TRY(cudaMemcpyAsync(p.p, points, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+        const size_t pb = n * 16 * limbs_of<F>::N;
+        DevBuf p(pb), s(n * 32);
+        CUDA_TRY(cudaMemcpyAsync(p.p, points, pb, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(s.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-        return b200_msm_g1_dev(ctx, p.u(), s.u(), n, out_affine);
-    } catch (const CudaErr &e) { return ctx_fail(ctx, B200_ERR_CUDA, "CUDA error in b200_msm_g1"); }
+        return msm_dev<F>(ctx, p.u(), s.u(), n, out_affine, who);
+    } catch (const CudaErr &e) { return ctx_fail(ctx, B200_ERR_CUDA, std::string("CUDA error in ") + who); }
+}
+
+}  // namespace
+
+extern "C" int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[8]) {
+    return msm_dev<fq>(ctx, d_points, d_scalars, n, out_affine, "b200_msm_g1");
+}
+extern "C" int b200_msm_g1(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[8]) {
+    return msm_host<fq>(ctx, points, scalars, n, out_affine, "b200_msm_g1");
+}
+extern "C" int b200_msm_g2_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[16]) {
+    return msm_dev<fq2>(ctx, d_points, d_scalars, n, out_affine, "b200_msm_g2");
+}
+extern "C" int b200_msm_g2(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[16]) {
+    return msm_host<fq2>(ctx, points, scalars, n, out_affine, "b200_msm_g2");
 }
