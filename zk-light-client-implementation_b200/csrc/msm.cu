@@ -54,7 +54,74 @@ GL_HD fq fq_sub(const fq &a, const fq &b) {
     return r;
 }
 #define FQ_FN static __host__ __device__ __noinline__
-FQ_FN fq fq_mul(const fq &a, const fq &b) {        // Montgomery CIOS
+#ifdef __CUDA_ARCH__
+// Device Montgomery multiplication on 32-bit limbs.  The 32x32->64 multiplier (IMAD.WIDE, 25 /clk/SM) is the scarce unit, so
+// the goal is the minimal 128 wide multiply-accumulates with carries riding in the flag instead of compare/select code.
+// T = E + (O << 32): a product x_j * y_i goes to E when j + i is even and to O when it is odd, so every product lands on an
+// aligned limb pair and one row of four products is a single carry chain.  Each of the 4 iterations consumes two limbs
+// of b, adds q * m with the 64-bit q that clears the low 64 bits, and shifts by 64 bits, which keeps the E/O parity.
+// (validated limb-for-limb against a Python model; bounds: E <= T < 2^320 inside an iteration, T < 2m after the shift)
+#define MAC_ROW(c0, c1, c2, c3, c4, c5, c6, c7, c8, x0, x1, x2, x3, y)                                                   \
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"  "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                     \
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t" "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"                                    \
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t" "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                    \
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t" "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                    \
+        "addc.u32 %8, %8, 0;"                                                                                            \
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7), "+r"(c8)                      \
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y))
+#define MAC_4ROWS(X, y0, y1)                                                                                             \
+    MAC_ROW(e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8], X[0], X[2], X[4], X[6], y0);                           \
+    MAC_ROW(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], X[1], X[3], X[5], X[7], y0);                           \
+    MAC_ROW(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], X[0], X[2], X[4], X[6], y1);                           \
+    MAC_ROW(e[2], e[3], e[4], e[5], e[6], e[7], e[8], e[9], e[10], X[1], X[3], X[5], X[7], y1)
+static __device__ __noinline__ fq fq_mul(const fq &A, const fq &B) {
+    const u32 m[8] = {(u32)Q0, (u32)(Q0 >> 32), (u32)Q1, (u32)(Q1 >> 32), (u32)Q2, (u32)(Q2 >> 32), (u32)Q3, (u32)(Q3 >> 32)};
+    u32 a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { a[2 * i] = (u32)A.v[i]; a[2 * i + 1] = (u32)(A.v[i] >> 32); b[2 * i] = (u32)B.v[i]; b[2 * i + 1] = (u32)(B.v[i] >> 32); }
+    u32 e[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        MAC_4ROWS(a, b[2 * i], b[2 * i + 1]);
+        const u64 q = ((u64)(e[1] + o[0]) << 32 | e[0]) * Q_INV;
+        const u32 q0 = (u32)q, q1 = (u32)(q >> 32);
+        MAC_4ROWS(m, q0, q1);
+        // low 64 bits of T are now zero; e[1] + o[0] is 0 or 2^32 and its carry belongs to limb 2, as does o[1].  Shift by 64.
+        u32 dummy;
+        asm("add.cc.u32 %8, %9, %10;\n\t" "addc.cc.u32 %0, %0, %11;\n\t" "addc.cc.u32 %1, %1, 0;\n\t" "addc.cc.u32 %2, %2, 0;\n\t"
+            "addc.cc.u32 %3, %3, 0;\n\t" "addc.cc.u32 %4, %4, 0;\n\t" "addc.cc.u32 %5, %5, 0;\n\t" "addc.cc.u32 %6, %6, 0;\n\t" "addc.u32 %7, %7, 0;"
+            : "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "=r"(dummy)
+            : "r"(e[1]), "r"(o[0]), "r"(o[1]));
+#pragma unroll
+        for (int k = 0; k < 8; k++) e[k] = e[k + 2];
+        e[8] = e[9] = e[10] = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) o[k] = o[k + 2];
+        o[7] = o[8] = 0;
+    }
+    // T = E + (O << 32) < 2m, then one conditional subtraction
+    u32 r[8]; r[0] = e[0];
+    asm("add.cc.u32 %0, %7, %14;\n\t" "addc.cc.u32 %1, %8, %15;\n\t" "addc.cc.u32 %2, %9, %16;\n\t" "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t" "addc.cc.u32 %5, %12, %19;\n\t" "addc.u32 %6, %13, %20;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]));
+    u32 t[8], borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t" "subc.cc.u32 %1, %10, %18;\n\t" "subc.cc.u32 %2, %11, %19;\n\t" "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t" "subc.cc.u32 %5, %14, %22;\n\t" "subc.cc.u32 %6, %15, %23;\n\t" "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7]));
+    fq out;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        u32 lo = borrow ? r[2 * i] : t[2 * i], hi = borrow ? r[2 * i + 1] : t[2 * i + 1];
+        out.v[i] = ((u64)hi << 32) | lo;
+    }
+    return out;
+}
+#else
+static fq fq_mul(const fq &a, const fq &b) {        // host: Montgomery CIOS on 64-bit limbs
     const u64 m[4] = {Q0, Q1, Q2, Q3};
     u64 t[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
@@ -70,6 +137,7 @@ FQ_FN fq fq_mul(const fq &a, const fq &b) {        // Montgomery CIOS
     if (t[4] || fq_geq(r.v)) fq_subq(r.v);
     return r;
 }
+#endif
 GL_HD fq fq_zero() { fq r; for (int i = 0; i < 4; i++) r.v[i] = 0; return r; }
 GL_HD bool fq_is_zero(const fq &a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
 GL_HD fq fq_to_mont(const u64 x[4]) {
@@ -212,6 +280,19 @@ __global__ void k_scatter(const u32 *__restrict__ digits, size_t n, const u32 *_
     u32 pos = atomicAdd(&cursor[win * NBUCKET + d], 1u);
     sorted[win * n + offsets[win * NBUCKET + d] + pos] = (u32)i;
 }
+// affine points, canonical limbs -> Montgomery limbs, once per MSM (every point is added into 16 buckets); the all-zero
+// encoding of the point at infinity is its own image
+__global__ void k_points_to_mont(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n_fq) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_fq) return;
+    u64 l[4] = {in[4 * i], in[4 * i + 1], in[4 * i + 2], in[4 * i + 3]};
+    fq x = fq_to_mont(l);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[4 * i + k] = x.v[k];
+}
+GL_HD void f_load_mont(fq &x, const u64 *p) { for (int i = 0; i < 4; i++) x.v[i] = p[i]; }
+GL_HD void f_load_mont(fq2 &x, const u64 *p) { f_load_mont(x.a, p); f_load_mont(x.b, p + 4); }
+
 template <class F>
 __global__ void __launch_bounds__(128) k_buckets(const u64 *__restrict__ points, size_t n, const u32 *__restrict__ counts, const u32 *__restrict__ offsets,
                                                  const u32 *__restrict__ sorted, xyzz_t<F> *__restrict__ buckets) {
@@ -228,7 +309,7 @@ __global__ void __launch_bounds__(128) k_buckets(const u64 *__restrict__ points,
 #pragma unroll
         for (int i = 0; i < 2 * NL; i++) { l[i] = p[i]; any |= l[i]; }
         if (any == 0) continue;                                                                 // point at infinity
-        F x, y; f_load(x, l); f_load(y, l + NL);
+        F x, y; f_load_mont(x, l); f_load_mont(y, l + NL);
         pt_madd(acc, x, y);
     }
     buckets[b] = acc;
@@ -293,18 +374,20 @@ static int msm_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_sc
         // all scratch comes from the context arena (cudaMalloc/cudaFree per call cost more than the kernels at 2^18 points)
         auto rnd = [](size_t b) { return (b + 255) & ~size_t(255); };
         const size_t sz_digits = rnd(n * NWIN * 4), sz_cnt = rnd((size_t)NWIN * NBUCKET * 4), sz_sorted = rnd(n * NWIN * 4),
-                     sz_buckets = rnd((size_t)NWIN * NBUCKET * sizeof(xyzz)), sz_chunks = rnd((size_t)NWIN * NCHUNK * sizeof(xyzz)), sz_wins = rnd(NWIN * sizeof(xyzz));
-        u8 *base = ctx_arena(ctx, sz_digits + 3 * sz_cnt + sz_sorted + sz_buckets + sz_chunks + sz_wins);
+                     sz_buckets = rnd((size_t)NWIN * NBUCKET * sizeof(xyzz)), sz_chunks = rnd((size_t)NWIN * NCHUNK * sizeof(xyzz)), sz_wins = rnd(NWIN * sizeof(xyzz)),
+                     sz_mont = rnd(n * 2 * NL * 8);
+        u8 *base = ctx_arena(ctx, sz_digits + 3 * sz_cnt + sz_sorted + sz_buckets + sz_chunks + sz_wins + sz_mont);
         struct Buf { void *p; size_t bytes; };
         size_t off = 0; auto take = [&](size_t b) { Buf r{base + off, b}; off += b; return r; };
         Buf digits = take(sz_digits), counts = take(sz_cnt), offsets = take(sz_cnt), cursor = take(sz_cnt), sorted = take(sz_sorted),
-            buckets = take(sz_buckets), chunks = take(sz_chunks), wins = take(sz_wins);
+            buckets = take(sz_buckets), chunks = take(sz_chunks), wins = take(sz_wins), mont = take(sz_mont);
         CUDA_TRY(cudaMemsetAsync(counts.p, 0, counts.bytes, st)); CUDA_TRY(cudaMemsetAsync(cursor.p, 0, cursor.bytes, st));
+        { PhaseTimer t(ctx, "msm_to_mont"); k_points_to_mont<<<(unsigned)((n * (NL / 2) + 255) / 256), 256, 0, st>>>(d_points, (u64 *)mont.p, n * (NL / 2)); LAUNCHED(1); }
         { PhaseTimer t(ctx, "msm_digits"); k_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scalars, n, (u32 *)digits.p, (u32 *)counts.p); LAUNCHED(1); }
         { PhaseTimer t(ctx, "msm_sort");
           k_scan<<<NWIN, 1024, 0, st>>>((const u32 *)counts.p, (u32 *)offsets.p); LAUNCHED(1);
           k_scatter<<<(unsigned)((n * NWIN + 255) / 256), 256, 0, st>>>((const u32 *)digits.p, n, (const u32 *)offsets.p, (u32 *)cursor.p, (u32 *)sorted.p); LAUNCHED(1); }
-        { PhaseTimer t(ctx, "msm_buckets"); k_buckets<F><<<(unsigned)(((size_t)NWIN * NBUCKET + 127) / 128), 128, 0, st>>>(d_points, n, (const u32 *)counts.p, (const u32 *)offsets.p, (const u32 *)sorted.p, (xyzz *)buckets.p); LAUNCHED(1); }
+        { PhaseTimer t(ctx, "msm_buckets"); k_buckets<F><<<(unsigned)(((size_t)NWIN * NBUCKET + 127) / 128), 128, 0, st>>>((const u64 *)mont.p, n, (const u32 *)counts.p, (const u32 *)offsets.p, (const u32 *)sorted.p, (xyzz *)buckets.p); LAUNCHED(1); }
         { PhaseTimer t(ctx, "msm_windows");
           k_window_chunks<F><<<(NWIN * NCHUNK + 63) / 64, 64, 0, st>>>((const xyzz *)buckets.p, (xyzz *)chunks.p); LAUNCHED(1);
           k_window_final<F><<<NWIN, 128, 0, st>>>((const xyzz *)chunks.p, (xyzz *)wins.p); LAUNCHED(1); }
