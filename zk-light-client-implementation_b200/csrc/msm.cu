@@ -14,6 +14,7 @@
 // Algorithmic bytes: 64 N (points) + 32 N (scalars); the bucket phase re-reads every point 16 times through L2.
 #include "../../include/b200_plonky2.h"
 #include "ctx.h"
+#include "mont256.cuh"
 #include <vector>
 
 namespace {
@@ -25,6 +26,7 @@ struct fq { u64 v[4]; };
 #define Q3 0x30644e72e131a029ULL
 #define Q_INV 0x87d20782e4866389ULL
 
+struct FqMod { static constexpr u64 M0 = Q0, M1 = Q1, M2 = Q2, M3 = Q3, INV = Q_INV; };
 GL_HD u64 mac64(u64 a, u64 b, u64 c, u64 &carry) {
     u64 lo, hi; gl_mul_wide(a, b, lo, hi);
     lo += c; hi += (lo < c);
@@ -41,12 +43,18 @@ GL_HD void fq_subq(u64 a[4]) {
     for (int i = 0; i < 4; i++) { u64 d = a[i] - m[i]; u64 b1 = a[i] < m[i]; u64 d2 = d - br; u64 b2 = d < br; a[i] = d2; br = b1 | b2; }
 }
 GL_HD fq fq_add(const fq &a, const fq &b) {
+#ifdef __CUDA_ARCH__
+    fq rr; mont256_add<FqMod>(a.v, b.v, rr.v); return rr;
+#endif
     fq r; u64 c = 0;
     for (int i = 0; i < 4; i++) { u64 s = a.v[i] + b.v[i]; u64 c1 = s < a.v[i]; u64 s2 = s + c; u64 c2 = s2 < s; r.v[i] = s2; c = c1 | c2; }
     if (c || fq_geq(r.v)) fq_subq(r.v);
     return r;
 }
 GL_HD fq fq_sub(const fq &a, const fq &b) {
+#ifdef __CUDA_ARCH__
+    fq rr; mont256_sub<FqMod>(a.v, b.v, rr.v); return rr;
+#endif
     const u64 m[4] = {Q0, Q1, Q2, Q3};
     fq r; u64 br = 0;
     for (int i = 0; i < 4; i++) { u64 d = a.v[i] - b.v[i]; u64 b1 = a.v[i] < b.v[i]; u64 d2 = d - br; u64 b2 = d < br; r.v[i] = d2; br = b1 | b2; }
@@ -54,75 +62,11 @@ GL_HD fq fq_sub(const fq &a, const fq &b) {
     return r;
 }
 #define FQ_FN static __host__ __device__ __noinline__
+FQ_FN fq fq_mul(const fq &a, const fq &b) {
 #ifdef __CUDA_ARCH__
-// Device Montgomery multiplication on 32-bit limbs.  The 32x32->64 multiplier (IMAD.WIDE, 25 /clk/SM) is the scarce unit, so
-// the goal is the minimal 128 wide multiply-accumulates with carries riding in the flag instead of compare/select code.
-// T = E + (O << 32): a product x_j * y_i goes to E when j + i is even and to O when it is odd, so every product lands on an
-// aligned limb pair and one row of four products is a single carry chain.  Each of the 4 iterations consumes two limbs
-// of b, adds q * m with the 64-bit q that clears the low 64 bits, and shifts by 64 bits, which keeps the E/O parity.
-// (validated limb-for-limb against a Python model; bounds: E <= T < 2^320 inside an iteration, T < 2m after the shift)
-#define MAC_ROW(c0, c1, c2, c3, c4, c5, c6, c7, c8, x0, x1, x2, x3, y)                                                   \
-    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"  "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                     \
-        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t" "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"                                    \
-        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t" "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                    \
-        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t" "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                    \
-        "addc.u32 %8, %8, 0;"                                                                                            \
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7), "+r"(c8)                      \
-        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y))
-#define MAC_4ROWS(X, y0, y1)                                                                                             \
-    MAC_ROW(e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8], X[0], X[2], X[4], X[6], y0);                           \
-    MAC_ROW(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], X[1], X[3], X[5], X[7], y0);                           \
-    MAC_ROW(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], X[0], X[2], X[4], X[6], y1);                           \
-    MAC_ROW(e[2], e[3], e[4], e[5], e[6], e[7], e[8], e[9], e[10], X[1], X[3], X[5], X[7], y1)
-static __device__ __noinline__ fq fq_mul(const fq &A, const fq &B) {
-    const u32 m[8] = {(u32)Q0, (u32)(Q0 >> 32), (u32)Q1, (u32)(Q1 >> 32), (u32)Q2, (u32)(Q2 >> 32), (u32)Q3, (u32)(Q3 >> 32)};
-    u32 a[8], b[8];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { a[2 * i] = (u32)A.v[i]; a[2 * i + 1] = (u32)(A.v[i] >> 32); b[2 * i] = (u32)B.v[i]; b[2 * i + 1] = (u32)(B.v[i] >> 32); }
-    u32 e[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        MAC_4ROWS(a, b[2 * i], b[2 * i + 1]);
-        const u64 q = ((u64)(e[1] + o[0]) << 32 | e[0]) * Q_INV;
-        const u32 q0 = (u32)q, q1 = (u32)(q >> 32);
-        MAC_4ROWS(m, q0, q1);
-        // low 64 bits of T are now zero; e[1] + o[0] is 0 or 2^32 and its carry belongs to limb 2, as does o[1].  Shift by 64.
-        u32 dummy;
-        asm("add.cc.u32 %8, %9, %10;\n\t" "addc.cc.u32 %0, %0, %11;\n\t" "addc.cc.u32 %1, %1, 0;\n\t" "addc.cc.u32 %2, %2, 0;\n\t"
-            "addc.cc.u32 %3, %3, 0;\n\t" "addc.cc.u32 %4, %4, 0;\n\t" "addc.cc.u32 %5, %5, 0;\n\t" "addc.cc.u32 %6, %6, 0;\n\t" "addc.u32 %7, %7, 0;"
-            : "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "=r"(dummy)
-            : "r"(e[1]), "r"(o[0]), "r"(o[1]));
-#pragma unroll
-        for (int k = 0; k < 8; k++) e[k] = e[k + 2];
-        e[8] = e[9] = e[10] = 0;
-#pragma unroll
-        for (int k = 0; k < 7; k++) o[k] = o[k + 2];
-        o[7] = o[8] = 0;
-    }
-    // T = E + (O << 32) < 2m, then one conditional subtraction
-    u32 r[8]; r[0] = e[0];
-    asm("add.cc.u32 %0, %7, %14;\n\t" "addc.cc.u32 %1, %8, %15;\n\t" "addc.cc.u32 %2, %9, %16;\n\t" "addc.cc.u32 %3, %10, %17;\n\t"
-        "addc.cc.u32 %4, %11, %18;\n\t" "addc.cc.u32 %5, %12, %19;\n\t" "addc.u32 %6, %13, %20;"
-        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]));
-    u32 t[8], borrow;
-    asm("sub.cc.u32 %0, %9, %17;\n\t" "subc.cc.u32 %1, %10, %18;\n\t" "subc.cc.u32 %2, %11, %19;\n\t" "subc.cc.u32 %3, %12, %20;\n\t"
-        "subc.cc.u32 %4, %13, %21;\n\t" "subc.cc.u32 %5, %14, %22;\n\t" "subc.cc.u32 %6, %15, %23;\n\t" "subc.cc.u32 %7, %16, %24;\n\t"
-        "subc.u32 %8, 0, 0;"
-        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
-        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]), "r"(m[6]), "r"(m[7]));
-    fq out;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        u32 lo = borrow ? r[2 * i] : t[2 * i], hi = borrow ? r[2 * i + 1] : t[2 * i + 1];
-        out.v[i] = ((u64)hi << 32) | lo;
-    }
-    return out;
-}
+    fq r; mont256_mul<FqMod>(a.v, b.v, r.v); return r;          // 32-bit-limb even/odd CIOS, mont256.cuh
 #else
-static fq fq_mul(const fq &a, const fq &b) {        // host: Montgomery CIOS on 64-bit limbs
-    const u64 m[4] = {Q0, Q1, Q2, Q3};
+    const u64 m[4] = {Q0, Q1, Q2, Q3};                           // host: Montgomery CIOS on 64-bit limbs
     u64 t[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
         u64 c = 0;
@@ -136,8 +80,8 @@ static fq fq_mul(const fq &a, const fq &b) {        // host: Montgomery CIOS on 
     fq r; for (int i = 0; i < 4; i++) r.v[i] = t[i];
     if (t[4] || fq_geq(r.v)) fq_subq(r.v);
     return r;
-}
 #endif
+}
 GL_HD fq fq_zero() { fq r; for (int i = 0; i < 4; i++) r.v[i] = 0; return r; }
 GL_HD bool fq_is_zero(const fq &a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) == 0; }
 GL_HD fq fq_to_mont(const u64 x[4]) {
@@ -184,8 +128,6 @@ static fq2 f_inv_host(const fq2 &x) {
     fq2 r; r.a = fq_mul(x.a, d); r.b = fq_sub(fq_zero(), fq_mul(x.b, d)); return r;
 }
 // affine coordinates <-> canonical little-endian limbs (4 per F_q element; F_q2 as a0 then a1, gnark-crypto's E2{A0, A1})
-GL_HD void f_load(fq &x, const u64 *p) { x = fq_to_mont(p); }
-GL_HD void f_load(fq2 &x, const u64 *p) { x.a = fq_to_mont(p); x.b = fq_to_mont(p + 4); }
 GL_HD void f_store(const fq &x, u64 *p) { fq_from_mont(x, p); }
 GL_HD void f_store(const fq2 &x, u64 *p) { fq_from_mont(x.a, p); fq_from_mont(x.b, p + 4); }
 template <class F> struct limbs_of { static constexpr int N = sizeof(F) / 8; };
