@@ -166,11 +166,18 @@ def run_b200(args):
         try:
             k = args.block_signatures
             rec_cd = wrap_cd = None
+            ready = 1
             if rank == 0:
-                rec_cd = workloads.build("rec", 13, seed=3); rec_cd.upload(ctx)
-                wrap_cd = workloads.build("rec", 12, seed=3, hasher="bn254"); wrap_cd.upload(ctx)
-                rec_w = ctx.pinned_copy(rec_cd.wires); wrap_w = ctx.pinned_copy(wrap_cd.wires)
-                rec_cd.prove(ctx, wires=rec_w); wrap_cd.prove(ctx, wires=wrap_w)
+                try:
+                    rec_cd = workloads.build("rec", 13, seed=3); rec_cd.upload(ctx)
+                    wrap_cd = workloads.build("rec", 12, seed=3, hasher="bn254"); wrap_cd.upload(ctx)
+                    rec_w = ctx.pinned_copy(rec_cd.wires); wrap_w = ctx.pinned_copy(wrap_cd.wires)
+                    rec_cd.prove(ctx, wires=rec_w); wrap_cd.prove(ctx, wires=wrap_w)
+                except Exception as e:
+                    ready = 0; print(f"[bench] block set-up failed on rank 0: {e}", file=sys.stderr)
+            if dist:      # every rank takes the same branch: a one-sided failure must not leave the others in a barrier
+                fl = torch.tensor([ready], dtype=torch.int64, device="cuda"); dist.all_reduce(fl, op=dist.ReduceOp.MIN); ready = int(fl.item())
+            if not ready: raise RuntimeError("block set-up failed")
             mine = sharding.shard_indices(k, world, rank)
             barrier(); t0 = time.perf_counter()
             recs = [sharding.digest_record(i, prove(False)) for i in mine]
