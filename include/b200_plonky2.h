@@ -158,6 +158,12 @@ int b200_msm_g1_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_s
  * out_affine: 16 u64 in the same order. */
 int b200_msm_g2(b200_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, uint64_t out_affine[16]);
 int b200_msm_g2_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_scalars, size_t n, uint64_t out_affine[16]);
+/* BN254 scalar-field NTT (the FFTs of groth16.Prove, gnark-crypto ecc/bn254/fr/fft: generator 5, 2-adicity 28):
+ * values / out: 2^log_n elements x 4 u64 (canonical little-endian limbs), natural order in and out.
+ * inverse = 0: A[k] = sum_i a[i] w^(ik)   (coset != 0: a[i] *= 5^i first, i.e. evaluation on the coset 5<w>)
+ * inverse = 1: a[i] = n^-1 sum_k A[k] w^(-ik)   (coset != 0: a[i] *= 5^-i afterwards).  log_n <= 28. */
+int b200_fr_ntt(b200_ctx *ctx, const uint64_t *values, uint32_t log_n, int inverse, int coset, uint64_t *out);
+int b200_fr_ntt_dev(b200_ctx *ctx, const uint64_t *d_values, uint32_t log_n, int inverse, int coset, uint64_t *d_out);
 /* Poseidon permutation of `count` independent 12-word states (self-test / throughput probe). */
 int b200_poseidon_permute(b200_ctx *ctx, uint64_t *states, size_t count);
 

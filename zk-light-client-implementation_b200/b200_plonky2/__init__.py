@@ -65,6 +65,8 @@ _sig("b200_msm_g1", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
 _sig("b200_msm_g1_dev", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
 _sig("b200_msm_g2", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
 _sig("b200_msm_g2_dev", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
+_sig("b200_fr_ntt", c_int, c_void_p, c_void_p, c_u32, c_int, c_int, c_void_p)
+_sig("b200_fr_ntt_dev", c_int, c_void_p, c_void_p, c_u32, c_int, c_int, c_void_p)
 _sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
 _sig("b200_verify_error", ctypes.c_char_p)
 
@@ -72,7 +74,7 @@ EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_c
            "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
            "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
            "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
-           "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev", "b200_msm_g2", "b200_msm_g2_dev"]
+           "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev", "b200_msm_g2", "b200_msm_g2_dev", "b200_fr_ntt", "b200_fr_ntt_dev"]
 
 def _np(a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
@@ -158,6 +160,14 @@ class Context:
         self._chk(lib.b200_msm_g2(self.h, pp, sp, p.shape[0], out.ctypes.data_as(c_void_p)))
         v = [sum(int(out[4 * k + i]) << (64 * i) for i in range(4)) for k in range(4)]
         return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
+    def fr_ntt(self, values, inverse=False, coset=False):
+        """values: [n][4] u64 canonical limbs of BN254 F_r elements (natural order) -> transformed [n][4]."""
+        a, p = _np(values)
+        n = a.shape[0]; log_n = n.bit_length() - 1
+        assert n == 1 << log_n and a.shape[1] == 4
+        out = np.zeros_like(a)
+        self._chk(lib.b200_fr_ntt(self.h, p, log_n, int(inverse), int(coset), out.ctypes.data_as(c_void_p)))
+        return out
     def poseidon_permute(self, states):
         a, p = _np(np.array(states, dtype=np.uint64, copy=True))
         self._chk(lib.b200_poseidon_permute(self.h, p, a.shape[0]))

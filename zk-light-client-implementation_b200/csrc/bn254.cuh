@@ -58,6 +58,16 @@ GL_HD fr_t fr_add(const fr_t &a, const fr_t &b) {
     if (c || fr_geq_mod(r.v)) fr_sub_mod(r.v);
     return r;
 }
+GL_HD fr_t fr_sub(const fr_t &a, const fr_t &b) {
+#ifdef __CUDA_ARCH__
+    fr_t rr; mont256_sub<FrMod>(a.v, b.v, rr.v); return rr;
+#endif
+    const u64 m[4] = {FR_M0, FR_M1, FR_M2, FR_M3};
+    fr_t r; u64 br = 0;
+    for (int i = 0; i < 4; i++) { u64 d = a.v[i] - b.v[i]; u64 b1 = a.v[i] < b.v[i]; u64 d2 = d - br; u64 b2 = d < br; r.v[i] = d2; br = b1 | b2; }
+    if (br) { u64 c = 0; for (int i = 0; i < 4; i++) { u64 s = r.v[i] + m[i]; u64 c1 = s < r.v[i]; u64 s2 = s + c; u64 c2 = s2 < s; r.v[i] = s2; c = c1 | c2; } }
+    return r;
+}
 // On the device fr_mul is ONE out-of-line function (the first build inlined it ~900 times: 25 k instructions per kernel,
 // instruction-fetch bound); loops over it stay rolled.
 #ifdef __CUDACC__

@@ -43,6 +43,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     ntt_tables_free(ctx->tw);
     for (auto &kv : ctx->lde_scale) cudaFree(kv.second);
     if (ctx->arena) cudaFree(ctx->arena);
+    for (int i = 0; i < 2; i++) if (ctx->fr_tw[i]) cudaFree(ctx->fr_tw[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -22,6 +22,7 @@ struct b200_ctx {
     u64 *tmp_q_big = nullptr;
     void *pinned = nullptr;                           // pinned staging for the small per-proof transfers
     cudaStream_t copy_stream = nullptr;               // H2D of host witnesses, overlapped with the LDE
+    void *fr_tw[2] = {nullptr, nullptr}; int fr_tw_log[2] = {0, 0};   // BN254 F_r twiddles (fr_ntt.cu): forward, inverse
     // optional phase timing (b200_ctx_enable_timing): CUDA events on the context stream around prover phases
     bool timing = false;
     std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> timing_events;
