@@ -219,6 +219,22 @@ GL_HD void poseidon_partial_rounds(u64 s[12]) {
 
 // in/out canonical
 GL_HD void poseidon_permute(u64 s[12]) {
+#ifndef __CUDA_ARCH__
+    // host (challenger, public-input hash, verifier): textbook rounds -- with the multiplier-free MDS a partial round costs one
+    // S-box + ~200 adds, cheaper on a CPU than the 23 full products of the sparse form below (3.0 vs 7.3 us per permutation)
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        const u64 *rc = PT(POSEIDON_RC) + 12 * r;
+        for (int i = 0; i < 12; i++) {
+            u64 c = rc[i], x = s[i] + c;
+            if (x < c) x += GL_EPS;
+            s[i] = (full || i == 0) ? poseidon_sbox(x) : x;
+        }
+        poseidon_mds(s);
+    }
+    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+    return;
+#endif
     poseidon_full_rounds(s, 0);
     poseidon_partial_rounds(s);
     poseidon_full_rounds(s, 12 * 26);
