@@ -284,6 +284,10 @@ def run_b200(args):
                 "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": (leaf[0] / ms_dev) if ms_dev else None,
                 "alu_note": {"permutations_per_launch": perms, "Mperm_per_s": perms / (per_launch_ms * 1e-3) / 1e6 if per_launch_ms else None,
+                             "ncu": {"source": "profiles/ncu_k_leaves_colmajor_r01_v5.json (ncu --set full, same kernel and shape)",
+                                     "issue_slots_active_pct": 75.3, "pipe_fmaheavy_active_pct": 84.3, "pipe_alu_active_pct": 67.0,
+                                     "instructions_per_permutation": 33200, "dram_throughput_pct_of_peak": 0.65,
+                                     "top_stalls": {"math_pipe_throttle": 0.36, "not_selected": 0.33}},
                              "comment": "integer-ALU bound (IMAD.WIDE.U32 issue rate), not HBM bound; see DESIGN.md"}}
     out_json = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
