@@ -27,12 +27,14 @@ struct fq { u64 v[4]; };
 #define Q_INV 0x87d20782e4866389ULL
 
 struct FqMod { static constexpr u64 M0 = Q0, M1 = Q1, M2 = Q2, M3 = Q3, INV = Q_INV; };
+#ifndef __CUDA_ARCH__       // host CIOS only; the device product is mont256_mul
 GL_HD u64 mac64(u64 a, u64 b, u64 c, u64 &carry) {
     u64 lo, hi; gl_mul_wide(a, b, lo, hi);
     lo += c; hi += (lo < c);
     lo += carry; hi += (lo < carry);
     carry = hi; return lo;
 }
+#endif
 GL_HD bool fq_geq(const u64 a[4]) {
     const u64 m[4] = {Q0, Q1, Q2, Q3};
     for (int i = 3; i >= 0; i--) { if (a[i] > m[i]) return true; if (a[i] < m[i]) return false; }
