@@ -84,12 +84,6 @@ __global__ void __launch_bounds__(128) k_fr_dif_pass(fr_t *__restrict__ data, co
     for (int e = 0; e < (1 << r); e++) p[(size_t)e << q] = x[e];
 }
 
-fr_t fr_pow_host(fr_t b, u64 e) {
-    const u64 one_c[4] = {1, 0, 0, 0};
-    fr_t r = fr_from_canonical(one_c);
-    while (e) { if (e & 1) r = fr_mul(r, b); b = fr_mul(b, b); e >>= 1; }
-    return r;
-}
 fr_t fr_inv_host(const fr_t &a) {          // Fermat
     u64 e[4] = {FR_M0 - 2, FR_M1, FR_M2, FR_M3};
     const u64 one_c[4] = {1, 0, 0, 0};
