@@ -6,6 +6,7 @@
 // `cols` elements costs ceil(cols/8) permutations (identity "hash" when cols <= 4); inner nodes cost one each.
 // Digest storage: level 0 (L x 4 u64) | level 1 (L/2 x 4) | ... | cap level (2^cap_height x 4).
 #include "b200_internal.h"
+#include <stdlib.h>
 #include "poseidon.cuh"
 
 #define MK_THREADS 128
@@ -159,6 +160,65 @@ __global__ void __launch_bounds__(128) k_leaves_rowmajor_quad(const u64 *__restr
         if (q == 1) digests[4 * leaf + 3] = s[0];
     }
 }
+// ---------------------------------------------------------------------------------------------------------------
+// TWELVE lanes per permutation (one state word per lane), for launches so small that only the latency of ONE permutation
+// matters (ncu on the quad form: ~28 us per tree level, ~470 dependent instructions per round per lane; here ~185: the lane
+// adds its round constant, raises its own word to the 7th power, and builds its MDS row from the other eleven words with
+// 22 shuffles and 24 wide multiply-accumulates).  A warp carries two permutations (lanes 0-11, 12-23); lanes 24-31 run the
+// same instructions on dummy data and never store.  Opt-in until it has been through the full GPU suite:
+// B200_MERKLE_LANES=12 in the environment.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 poseidon_permute_x12(u64 x, const int w, const int base) {
+    const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        const u64 c = d_POSEIDON_RC[12 * r + w];
+        u64 v = x + c;
+        if (v < c) v += GL_EPS;
+        if (full || w == 0) v = poseidon_sbox(v);
+        const u32 lo = (u32)v, hi = (u32)(v >> 32);
+        u64 al = 0, ah = 0;
+        int src = w;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            const u32 nl = __shfl_sync(0xffffffffu, lo, base + src), nh = __shfl_sync(0xffffffffu, hi, base + src);
+            al += (u64)nl * C[i]; ah += (u64)nh * C[i];
+            if (++src == 12) src = 0;
+        }
+        if (w == 0) { al += (u64)lo * 8u; ah += (u64)hi * 8u; }      // MDS diagonal
+        x = poseidon_reduce96(al, ah);
+    }
+    return gl_canon(x);
+}
+#define X12_PER_BLOCK 8            /* 4 warps x 2 permutations */
+__global__ void __launch_bounds__(128) k_merkle_level_x12(const u64 *__restrict__ in, u64 *__restrict__ out, size_t n_out) {
+    const int lane = threadIdx.x & 31, g = lane / 12, w = lane - 12 * g, base = 12 * g;
+    size_t node = (size_t)blockIdx.x * X12_PER_BLOCK + (threadIdx.x >> 5) * 2 + g;
+    const bool active = g < 2 && node < n_out;
+    if (node >= n_out) node = n_out - 1;
+    u64 x = (w < 8) ? in[8 * node + w] : 0;
+    x = poseidon_permute_x12(x, w, base);
+    if (active && w < 4) out[4 * node + w] = x;
+}
+__global__ void __launch_bounds__(128) k_leaves_rowmajor_x12(const u64 *__restrict__ data, size_t width, size_t L, u64 *__restrict__ digests) {
+    const int lane = threadIdx.x & 31, g = lane / 12, w = lane - 12 * g, base = 12 * g;
+    size_t leaf = (size_t)blockIdx.x * X12_PER_BLOCK + (threadIdx.x >> 5) * 2 + g;
+    const bool active = g < 2 && leaf < L;
+    if (leaf >= L) leaf = L - 1;
+    const u64 *row = data + leaf * width;
+    u64 x = 0;
+    for (size_t c = 0; c < width; c += 8) {
+        if (w < 8 && c + w < width) x = row[c + w];
+        x = poseidon_permute_x12(x, w, base);
+    }
+    if (active && w < 4) digests[4 * leaf + w] = x;
+}
+static int merkle_lanes() {        // 4 (default) or 12 (B200_MERKLE_LANES=12)
+    static const int v = [] { const char *e = getenv("B200_MERKLE_LANES"); return (e && atoi(e) == 12) ? 12 : 4; }();
+    return v;
+}
+#define X12_MAX_NODES 4096          /* above this the quad form's throughput wins */
+
 #define QUAD_MAX_NODES (size_t(148) * 16 * 32 / 4)      /* below ~19 k permutations a launch cannot fill the machine thread-per-permutation */
 
 void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digests, cudaStream_t st) {
@@ -168,7 +228,8 @@ void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digest
 }
 void merkle_leaves_rowmajor(const u64 *data, size_t width, int log_L, u64 *digests, cudaStream_t st) {
     size_t L = size_t(1) << log_L;
-    if (width > 4 && L <= QUAD_MAX_NODES) k_leaves_rowmajor_quad<<<(unsigned)((4 * L + 127) / 128), 128, 0, st>>>(data, width, L, digests);
+    if (width > 4 && L <= X12_MAX_NODES && merkle_lanes() == 12) k_leaves_rowmajor_x12<<<(unsigned)((L + X12_PER_BLOCK - 1) / X12_PER_BLOCK), 128, 0, st>>>(data, width, L, digests);
+    else if (width > 4 && L <= QUAD_MAX_NODES) k_leaves_rowmajor_quad<<<(unsigned)((4 * L + 127) / 128), 128, 0, st>>>(data, width, L, digests);
     else k_leaves_rowmajor<<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, width, L, digests);
     LAUNCHED(1);
 }
@@ -177,7 +238,8 @@ void merkle_build(u64 *digests, int log_L, int cap_height, cudaStream_t st) {
     for (int lv = log_L; lv > cap_height; lv--) {
         size_t n = size_t(1) << lv;
         u64 *nxt = cur + 4 * n;
-        if (n / 2 <= QUAD_MAX_NODES) k_merkle_level_quad<<<(unsigned)((4 * (n / 2) + 127) / 128), 128, 0, st>>>(cur, nxt, n / 2);
+        if (n / 2 <= X12_MAX_NODES && merkle_lanes() == 12) k_merkle_level_x12<<<(unsigned)((n / 2 + X12_PER_BLOCK - 1) / X12_PER_BLOCK), 128, 0, st>>>(cur, nxt, n / 2);
+        else if (n / 2 <= QUAD_MAX_NODES) k_merkle_level_quad<<<(unsigned)((4 * (n / 2) + 127) / 128), 128, 0, st>>>(cur, nxt, n / 2);
         else k_merkle_level<<<(unsigned)((n / 2 + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(cur, nxt, n / 2);
         LAUNCHED(1);
         cur = nxt;
