@@ -165,8 +165,9 @@ __global__ void __launch_bounds__(128) k_leaves_rowmajor_quad(const u64 *__restr
 // matters (ncu on the quad form: ~28 us per tree level, ~470 dependent instructions per round per lane; here ~185: the lane
 // adds its round constant, raises its own word to the 7th power, and builds its MDS row from the other eleven words with
 // 22 shuffles and 24 wide multiply-accumulates).  A warp carries two permutations (lanes 0-11, 12-23); lanes 24-31 run the
-// same instructions on dummy data and never store.  Opt-in until it has been through the full GPU suite:
-// B200_MERKLE_LANES=12 in the environment.
+// same instructions on dummy data and never store.  Opt-in (B200_MERKLE_LANES=12 in the environment) until it has been
+// through the full GPU suite: the kernel-level parity tests pass with it and a recursion-sized proof spends 0.26 ms less
+// in its Merkle launches (profiles/phase_rec13_r01_v9_x12_optin.json); the prover-level run is still outstanding.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ u64 poseidon_permute_x12(u64 x, const int w, const int base) {
     const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
