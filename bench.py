@@ -28,42 +28,76 @@ def workload_desc(log_n):
             "degree_bits": log_n, "num_wires": 234, "proofs_per_step_per_gpu": 1,
             "l2": "inputs larger than L2: the witness is 8*234*2^degree_bits bytes (245 MB at 2^17) and every pass streams GBs"}
 
-def cpu_sample(sample_log_n, full_log_n, threads=None, check_ctx=None):
-    """Oracle CPU prover on a bounded sample; returns (proofs/s scaled to the full size, info)."""
-    from b200_plonky2 import workloads
+def _host_threads():
+    """threads the CPU legs may use: the cores this process is allowed on (not os.cpu_count(): an affinity mask smaller than
+    the machine with one OpenMP thread per *machine* core oversubscribes and the spinning waiters make timings 10x unstable)."""
+    try: return max(1, len(os.sched_getaffinity(0)))
+    except Exception: return os.cpu_count() or 1
+
+def _omp_env(threads):
+    env = {"OMP_NUM_THREADS": str(threads), "OMP_WAIT_POLICY": "passive", "OMP_PROC_BIND": "false", "OMP_DYNAMIC": "false"}
+    os.environ.update(env)          # read by libgomp when liboracle.so is first loaded (before any oracle import)
+    return env
+
+def cpu_prover(kind, log_n, seed, hasher="gl", threads=None):
+    """The CPU arm: the C oracle prover (a port of upstream plonky2's prove(); the Rust reference cannot be built here) on the
+    circuit workloads.build(kind, log_n, seed) -- the SAME circuit and witness the GPU arm proves.  Returns (prove_fn, info);
+    the build-side commitment (OracleCircuit) is outside every timed region, as b200_circuit_upload is in the GPU arm."""
+    threads = threads or _host_threads()
+    env = _omp_env(threads)
+    from b200_plonky2 import workloads          # pure numpy: does not map libb200plonky2.so (b200_plonky2/__init__.py)
     from oracle import prover as oprover
-    os.environ["OMP_NUM_THREADS"] = str(threads or os.cpu_count() or 1)     # torchrun pins it to 1 otherwise
-    cd = workloads.build("sig", sample_log_n, seed=7)
-    oc = oprover.OracleCircuit(cd.common, cd.constants_sigmas)
+    cd = workloads.build(kind, log_n, seed=seed, hasher=hasher)
     t0 = time.time()
-    pb = oc.prove(cd.wires, cd.public_inputs)
-    dt = time.time() - t0
-    scale = 2 ** (full_log_n - sample_log_n)
-    info = {"sample": f"1 oracle-prover proof of the same circuit family at degree_bits {sample_log_n} "
-                      f"({dt:.2f} s), scaled x{scale} in rows to degree_bits {full_log_n}",
-            "sample_seconds": round(dt, 3)}
-    if check_ctx is not None:
-        gpu = cd.prove(check_ctx)
-        info["parity_check"] = "gpu proof bytes == oracle proof bytes" if gpu == pb else "MISMATCH"
-        cd.free()
-    return 1.0 / (dt * scale), info
+    oc = oprover.OracleCircuit(cd.common, cd.constants_sigmas)
+    t_build = time.time() - t0
+    def prove():
+        t = time.time(); pb = oc.prove(cd.wires, cd.public_inputs); return time.time() - t, pb
+    return prove, cd, {"threads": threads, "omp_env": env, "constants_sigmas_commit_s": round(t_build, 3)}
 
 def run_reference(args):
+    """--impl reference: the CPU prover on the box's host cores, on the headline circuit itself (not a smaller sample):
+    every step is one complete 2^log_n x 234 proof.  One untimed warm-up proof; if K full proofs do not fit the time budget
+    the arm times as many as fit and says so in `steps` (never extrapolates)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    sample = min(args.cpu_sample_log_n, args.log_n)
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        v, info = cpu_sample(sample, args.log_n)
-        vals.append(v)
-    v = sum(vals) / len(vals)
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
-           "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+    import hashlib
+    prove, cd, info = cpu_prover("sig", args.log_n, seed=1)
+    t_warm, pb = prove()                                   # warm-up (page faults of the first large allocations, thread team start)
+    steps = args.steps if args.steps * t_warm <= args.ref_budget_s else max(1, int(args.ref_budget_s // t_warm))
+    times = []
+    for _ in range(steps):
+        dt, pb = prove(); times.append(dt)
+    total = sum(times)
+    v = steps / total
+    # the other proof shapes of a block, for a CPU figure beside bft_finality_block (composed from measured per-proof times)
+    block = None
+    if not args.no_block:
+        try:
+            p_rec, _, _ = cpu_prover("rec", 13, seed=3); p_rec(); t_rec = min(p_rec()[0] for _ in range(2))
+            p_wrap, _, _ = cpu_prover("rec", 12, seed=3, hasher="bn254"); t_wrap = p_wrap()[0]
+            k = args.block_signatures
+            block = {"bft_block_ms": round((k * total / steps + (k + 55) * t_rec + t_wrap) * 1e3, 1), "composed": True,
+                     "sig_proof_ms": round(total / steps * 1e3, 1), "recursive_proof_2^13_ms": round(t_rec * 1e3, 1), "bn128_wrap_2^12_ms": round(t_wrap * 1e3, 1),
+                     "signatures": k, "recursive_proofs": k + 55,
+                     "note": "k sig-shaped + (k+55) recursive_proof-shaped + 1 BN128-wrap proofs, each timed on this host (all cores per proof, one at a "
+                             "time) and summed -- the whole block is not run end to end on the CPU (it would take > 10 min)"}
+        except Exception as e:
+            block = {"bft_block_ms": None, "error": str(e)}
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+           "ms_per_step": 1000.0 * total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
            "data": "synthetic", "config": workload_desc(args.log_n),
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", **info},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "port",
+                            "sample": f"{steps} complete oracle-prover proofs of the headline circuit itself (degree_bits {args.log_n}, 234 wires, seed 1), "
+                                      f"{total / steps:.2f} s each (min {min(times):.2f}, max {max(times):.2f}); warm-up proof {t_warm:.2f} s; "
+                                      "a C/OpenMP port of upstream plonky2's prove(), NOT the Rust prover (no toolchain in the image)",
+                            "step_seconds": [round(t, 3) for t in times], **info},
+           "proof_sha256": hashlib.sha256(pb).hexdigest(), "proof_bytes": len(pb),
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if steps != args.steps:
+        out["steps_note"] = f"{args.steps} steps requested; {steps} complete proofs fit the {args.ref_budget_s:.0f} s budget of this arm"
+    if block is not None: out["bft_finality_block"] = block
     print(json.dumps(out))
 
 class ClockSampler(threading.Thread):
@@ -113,12 +147,12 @@ def run_b200(args):
     pis = np.array(cd.public_inputs, dtype=np.uint64)
     out = ctypes.POINTER(ctypes.c_uint8)(); ln = c_size_t()
     proof_len = [0]
-    def prove(dev):
+    def prove(dev, full=False):
         fn = lib.b200_prove_dev if dev else lib.b200_prove
         ptr = dev_wires.data_ptr() if dev else host_wires.data_ptr()
         rc = fn(ctx.h, cd._handle, c_void_p(ptr), pis.ctypes.data_as(c_void_p), len(pis), ctypes.c_uint64(0), ctypes.byref(out), ctypes.byref(ln))
         if rc: raise RuntimeError(lib.b200_last_error(ctx.h).decode())
-        b = ctypes.string_at(out, 64); proof_len[0] = ln.value
+        b = ctypes.string_at(out, ln.value if full else 64); proof_len[0] = ln.value
         lib.b200_free(out)
         return b
     def barrier():
@@ -191,6 +225,16 @@ def run_b200(args):
     for _ in range(min(args.warmup, 1)): prove(False)
     ms_e2e = timed(False, args.steps, True)
     sampler.stop = True; sampler.join(timeout=2)
+
+    # ---- the proofs the timed loops produce are checked at the headline size, on every rank: the product's own verifier
+    # (b200_verify, host only) must accept the device-resident and the host-buffer proof, and both must be the same bytes
+    import hashlib
+    proof_dev, proof_host = prove(True, full=True), prove(False, full=True)
+    ok_verify = int(bool(cd.verify(proof_dev)) and proof_dev == proof_host)
+    if dist:
+        fl = torch.tensor([ok_verify], dtype=torch.int64, device="cuda"); dist.all_reduce(fl, op=dist.ReduceOp.MIN); ok_verify = int(fl.item())
+    if not ok_verify:
+        raise SystemExit("bench: a proof of the headline circuit was rejected by b200_verify (or dev/host proofs differ) -- no number reported")
 
     # ---- one whole BFT-finality block, measured (second half of BASELINE.json's metric; configs[1] at N=1, configs[2] at N=8):
     # k signed approvals -> k sig-shaped sub-proofs sharded round-robin over the ranks (host witnesses through b200_prove),
@@ -340,12 +384,29 @@ def run_b200(args):
             aux["bft_block_estimate_note"] = ("k=73 signed approvals (prove_random fixture): k sig-shaped proofs + (k+55) recursive_proof-shaped proofs + 1 BN128 wrap, "
                                               "prover time only (no witness generation / circuit builds, which stay in Rust); SHA-256 sub-proofs not included")
         out_json["aux_proof_shapes"] = aux
+    out_json["headline_proof_check"] = {"b200_verify": "accepted on every rank", "dev_bytes_equal_host_bytes": True,
+                                        "proof_sha256": hashlib.sha256(proof_dev).hexdigest(), "degree_bits": args.log_n}
     if world == 1 and not args.no_cpu_baseline:
+        # CPU baseline leg = ONE complete oracle-prover proof of the headline circuit itself (same circuit, same witness), which is
+        # also the parity check at the benchmark config: the GPU proof must be byte-identical to it.
+        threads = _host_threads(); env = _omp_env(threads)
         try:
-            v, info = cpu_sample(min(args.cpu_sample_log_n, args.log_n), args.log_n, check_ctx=ctx)
-            out_json["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", **info}
+            from oracle import prover as oprover
+            oc = oprover.OracleCircuit(cd.common, cd.constants_sigmas)
+            t0 = time.time(); pb = oc.prove(cd.wires, cd.public_inputs); dt = time.time() - t0
+            same = pb == proof_dev
+            out_json["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port", "omp_env": env,
+                                        "sample": f"1 complete oracle-prover proof of the headline circuit itself (degree_bits {args.log_n}, 234 wires): {dt:.2f} s "
+                                                  "(first proof in this process, no warm-up; the --impl reference arm times warmed-up proofs)",
+                                        "sample_seconds": round(dt, 3),
+                                        "parity_check": "gpu proof bytes == oracle proof bytes at the headline config" if same else "MISMATCH"}
+            out_json["headline_proof_check"]["bytes_equal_oracle_prover"] = bool(same)
+            if not same:
+                raise SystemExit("bench: GPU proof bytes differ from the oracle prover's at the headline config -- no number reported")
+        except SystemExit:
+            raise
         except Exception as e:       # the baseline is reported, never the product path
-            out_json["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e}"}
+            out_json["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"failed: {e}"}
     sys.stdout.flush(); os.dup2(real_stdout, 1)
     print(json.dumps(out_json), flush=True)
     if dist: dist.destroy_process_group()
@@ -357,7 +418,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=17)
-    ap.add_argument("--cpu-sample-log-n", type=int, default=14)
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the timed proofs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--no-block", action="store_true", help="skip the measured whole-block run (k sig proofs + fold + wrap)")

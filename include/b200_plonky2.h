@@ -35,7 +35,8 @@ typedef enum {
     B200_OK = 0,
     B200_ERR_BAD_ARG = -1,
     B200_ERR_CUDA = -2,
-    B200_ERR_UNSATISFIED = -3,   /* witness does not satisfy the circuit (quotient not a polynomial) */
+    B200_ERR_UNSATISFIED = -3,   /* witness does not satisfy the circuit: the permutation grand product is not 1 (copy constraint
+                                    violated) or the vanishing identity fails at zeta (a gate constraint is violated) */
     B200_ERR_OOM = -4,
     B200_ERR_UNSUPPORTED = -5,   /* e.g. unknown gate id, zero-knowledge blinding, lookups */
     B200_ERR_INVALID_PROOF = -6  /* b200_verify: the proof does not verify */
@@ -60,7 +61,7 @@ typedef struct {
     uint32_t num_partial_products;
     uint32_t num_gate_constraints;
     uint32_t num_public_inputs;
-    uint32_t hasher;                 /* 0 = PoseidonGoldilocksConfig; 1 = PoseidonBN128GoldilocksConfig (not yet) */
+    uint32_t hasher;                 /* 0 = PoseidonGoldilocksConfig; 1 = PoseidonBN128GoldilocksConfig (the final wrap) */
     uint32_t num_reduction_arity_bits;
     uint32_t reduction_arity_bits[16];
     uint32_t num_gates;

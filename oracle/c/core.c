@@ -10,6 +10,7 @@
 #include "poseidon_constants.h"
 #include <stdlib.h>
 #include <string.h>
+#include <omp.h>
 
 static inline u64 sbox7(u64 x) { u64 x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x2, x); return gl_mul(x4, x3); }
 
@@ -158,6 +159,10 @@ void orc_merkle_rowmajor(const u64 *data, size_t width, int log_L, int cap_heigh
 /* ---------- NTT: natural in -> natural out, in place ---------- */
 void orc_ntt(u64 *a, int log_n, int inverse) {
     size_t n = 1ULL << log_n;
+    /* a single large transform called outside a parallel region (the extension-field FRI polynomials) spreads its
+     * butterflies over the team; inside the per-column batches the threads are already busy */
+    const int par = !omp_in_parallel() && log_n >= 14;
+    #pragma omp parallel for schedule(static) if(par)
     for (size_t i = 0; i < n; i++) { size_t j = bitrev(i, log_n); if (i < j) { u64 t = a[i]; a[i] = a[j]; a[j] = t; } }
     u64 w_n = gl_root(log_n);
     if (inverse) w_n = gl_inv(w_n);
@@ -166,11 +171,12 @@ void orc_ntt(u64 *a, int log_n, int inverse) {
         u64 wm = gl_pow(w_n, n >> s);
         u64 *tw = (u64 *)malloc(h * sizeof(u64));
         tw[0] = 1; for (size_t k = 1; k < h; k++) tw[k] = gl_mul(tw[k - 1], wm);
-        for (size_t k = 0; k < n; k += m)
-            for (size_t j = 0; j < h; j++) {
-                u64 t = gl_mul(tw[j], a[k + j + h]), u = a[k + j];
-                a[k + j] = gl_add(u, t); a[k + j + h] = gl_sub(u, t);
-            }
+        #pragma omp parallel for schedule(static) if(par)
+        for (size_t b = 0; b < n / 2; b++) {
+            size_t j = b & (h - 1), k = (b >> (s - 1)) << s;
+            u64 t = gl_mul(tw[j], a[k + j + h]), u = a[k + j];
+            a[k + j] = gl_add(u, t); a[k + j + h] = gl_sub(u, t);
+        }
         free(tw);
     }
     if (inverse) { u64 ninv = gl_inv(n % GL_P); for (size_t i = 0; i < n; i++) a[i] = gl_mul(a[i], ninv); }

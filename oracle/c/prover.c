@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <omp.h>
 
 void orc_poseidon_permute(u64 s[12]);
 void orc_hash_no_pad(const u64 *in, size_t n, u64 out[4]);
@@ -263,14 +264,15 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
     e2 *open_next = (e2 *)malloc(nch * sizeof(e2));
     e2 gzeta = e2_scale(zeta, w_n);
     {
-        size_t idx = 0;
-        for (int o = 0; o < 4; o++)
-            for (size_t p = 0; p < oracles[o]->cols; p++, idx++) {
-                const u64 *cf = oracles[o]->coeffs + p * n;
-                e2 acc = { 0, 0 };
-                for (size_t kx = n; kx-- > 0;) { acc = e2_mul(acc, zeta); acc.a = gl_add(acc.a, cf[kx]); }
-                open_zeta[idx] = acc;
-            }
+        /* one Horner evaluation per polynomial (upstream: PolynomialBatch::eval via rayon over the polynomials) */
+        #pragma omp parallel for schedule(dynamic, 4)
+        for (size_t idx = 0; idx < total_polys; idx++) {
+            size_t q = idx; int o = 0; while (q >= oracles[o]->cols) { q -= oracles[o]->cols; o++; }
+            const u64 *cf = oracles[o]->coeffs + q * n;
+            e2 acc = { 0, 0 };
+            for (size_t kx = n; kx-- > 0;) { acc = e2_mul(acc, zeta); acc.a = gl_add(acc.a, cf[kx]); }
+            open_zeta[idx] = acc;
+        }
         for (uint32_t ci = 0; ci < nch; ci++) {
             const u64 *cf = zsb.coeffs + (size_t)ci * n;
             e2 acc = { 0, 0 };
@@ -346,6 +348,7 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         int ab = (int)c->arity_bits[li]; size_t arity = 1ULL << ab;
         /* reverse_index_bits_in_place(values) ; leaves = chunks of `arity` ext values flattened */
         u64 *leaves = (u64 *)malloc(cur_len * 16);
+        #pragma omp parallel for schedule(static)
         for (size_t i = 0; i < cur_len; i++) { size_t r = bitrev(i, cur_log); leaves[2 * r] = values[i].a; leaves[2 * r + 1] = values[i].b; }
         if (li == 0 && dbg && dbg->fri_values0) memcpy(dbg->fri_values0, leaves, cur_len * 16);
         int logleaves = cur_log - ab;
@@ -359,11 +362,14 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         if (dbg) { dbg->fri_betas[li][0] = beta.a; dbg->fri_betas[li][1] = beta.b; }
         /* coeffs = chunks(arity).map(reduce_with_powers(chunk, beta)) */
         size_t new_len = cur_len >> ab;
+        e2 *folded = (e2 *)malloc(new_len * sizeof(e2));
+        #pragma omp parallel for schedule(static)
         for (size_t i = 0; i < new_len; i++) {
             e2 acc = { 0, 0 };
             for (size_t j = arity; j-- > 0;) acc = e2_add(e2_mul(acc, beta), coeffs[i * arity + j]);
-            coeffs[i] = acc;
+            folded[i] = acc;
         }
+        memcpy(coeffs, folded, new_len * sizeof(e2)); free(folded);
         shift = gl_pow(shift, arity);
         cur_len = new_len; cur_log -= ab;
         COSET_FFT(cur_log);
@@ -382,9 +388,15 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
             chal t = base; ch_observe(&t, pow_hint);
             if ((ch_get(&t) >> (64 - c->pow_bits)) == 0) { pow_witness = pow_hint; found = 1; }
         }
-        for (u64 cand = 0; !found; cand++) {
-            chal t = base; ch_observe(&t, cand);
-            if ((ch_get(&t) >> (64 - c->pow_bits)) == 0) { pow_witness = cand; found = 1; }
+        /* minimum nonce: scan windows of 2^14 candidates in parallel, keep the smallest hit of the first window that has one */
+        for (u64 start = 0; !found; start += 1u << 14) {
+            u64 best = ~0ULL;
+            #pragma omp parallel for schedule(static) reduction(min : best)
+            for (u64 cand = start; cand < start + (1u << 14); cand++) {
+                chal t = base; ch_observe(&t, cand);
+                if ((ch_get(&t) >> (64 - c->pow_bits)) == 0 && cand < best) best = cand;
+            }
+            if (best != ~0ULL) { pow_witness = best; found = 1; }
         }
         ch_observe(&ch, pow_witness);
         u64 resp = ch_get(&ch);

@@ -84,6 +84,39 @@ def test_unsatisfied_witness_is_reported(ctx):
     assert e.value.code == -3                      # B200_ERR_UNSATISFIED
     cd.free()
 
+def test_violated_gate_constraint_is_reported(ctx):
+    """A witness that breaks a GATE constraint but no copy constraint keeps every committed polynomial low-degree (the
+    quotient is interpolated from its coset values) and the grand product at 1: only the vanishing identity at zeta sees
+    it.  b200_prove checks its own openings and must refuse to emit the proof (the verifiers reject the oracle's)."""
+    import b200_plonky2
+    from b200_plonky2 import workloads
+    from oracle import prover, proof_io as io, verifier
+    cd = workloads.build("tiny", 5, seed=4)
+    w = cd.wires.copy()
+    w[1, 31] ^= 1                                  # wire 1 of a ConstantGate row: not routed to anything
+    oc = prover.OracleCircuit(cd.common, cd.constants_sigmas)
+    bad = oc.prove(w, cd.public_inputs)            # the CPU restatement (like upstream) emits it ...
+    ok, why = b200_plonky2.verify(cd.common, oc.cap, oc.digest, bad)
+    assert not ok and "vanishing" in why           # ... and verification fails at the identity, not in FRI
+    cd.upload(ctx)
+    with pytest.raises(b200_plonky2.B200Error) as e:
+        cd.prove(ctx, wires=w)
+    assert e.value.code == -3 and "gate constraint" in str(e.value)
+    assert cd.prove(ctx) == oc.prove(cd.wires, cd.public_inputs)      # the context stays usable
+    cd.free()
+
+@pytest.mark.parametrize("db", [17, 18])
+def test_headline_config_proof_bytes_equal_oracle(ctx, db):
+    """The benchmark configuration itself (sig-shaped, 234 wires, 2^17 rows; 2^18 = the upper estimate for the real ed25519
+    circuit): W*N = 2.4e8 / 4.9e8 words, > 4 GB byte offsets.  GPU bytes == oracle prover bytes, both verifiers accept."""
+    from oracle import prover, proof_io as io, verifier
+    cd, oc, gpu, cpu = _prove_both(ctx, "sig", db, seed=1)
+    assert cd.verify(gpu)
+    cdo = prover.common_data(cd.common)
+    assert verifier.verify(cdo, oc.verifier_only(), io.proof_from_bytes(gpu, cdo))
+    assert gpu == cpu, "GPU proof bytes differ from the oracle prover's at the headline config"
+    cd.free()
+
 def test_pow_hint(ctx):
     from b200_plonky2 import workloads
     from oracle import prover, proof_io as io

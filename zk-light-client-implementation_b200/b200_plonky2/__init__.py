@@ -1,220 +1,22 @@
-"""ctypes binding of libb200plonky2.so (the C ABI in include/b200_plonky2.h) and a thin host-side mirror of the
-reference's plonky2 surface for the hot path (CircuitData.prove / verify-less; see circuit_data.py).
+"""Host-side mirror of the reference's plonky2 surface for the hot path (CircuitBuilder.build() -> CircuitData,
+CircuitData.prove / verify: circuit_builder.py) over the C ABI of libb200plonky2.so (native.py).
 
-The CUDA library is the only implementation: importing this package without the built .so, or creating a
-Context without a CUDA device, raises -- there is no CPU fallback.
+The CUDA library is the only implementation: anything that proves, verifies or touches a Context goes through
+`b200_plonky2.native`, whose import raises if the .so is not built -- there is no CPU fallback.  The binding is
+loaded on first use of one of its names (PEP 562) so that the pure-Python circuit/workload generators
+(circuit_builder, workloads: numpy only) can be imported by the CPU reference arm of bench.py without mapping the
+product library into that process.
 """
-import ctypes, os
-import numpy as np
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libb200plonky2.so")
+import importlib, os
 
-class B200Error(RuntimeError):
-    def __init__(self, code, msg):
-        super().__init__(f"libb200plonky2 error {code}: {msg}")
-        self.code = code
+_SUBMODULES = {f[:-3] for f in os.listdir(os.path.dirname(os.path.abspath(__file__))) if f.endswith(".py") and f != "__init__.py"}
 
-def _load():
-    if not os.path.exists(_LIB_PATH):
-        raise ImportError(f"{_LIB_PATH} not built: run zk-light-client-implementation_b200/build.sh "
-                          "(or __graft_entry__.build()); there is no CPU fallback")
-    return ctypes.CDLL(_LIB_PATH)
-
-lib = _load()
-u64p = ctypes.POINTER(ctypes.c_uint64)
-c_void_p, c_size_t, c_int, c_u32, c_u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64
-
-class Common(ctypes.Structure):
-    _fields_ = [(n, c_u32) for n in (
-        "num_wires", "num_routed_wires", "num_constants", "num_challenges", "degree_bits", "rate_bits", "cap_height",
-        "proof_of_work_bits", "num_query_rounds", "quotient_degree_factor", "num_partial_products",
-        "num_gate_constraints", "num_public_inputs", "hasher", "num_reduction_arity_bits")] + [
-        ("reduction_arity_bits", c_u32 * 16), ("num_gates", c_u32),
-        ("gate_ids", ctypes.POINTER(ctypes.c_char_p)), ("selector_indices", ctypes.POINTER(c_u32)),
-        ("num_selector_groups", c_u32), ("group_starts", ctypes.POINTER(c_u32)), ("group_ends", ctypes.POINTER(c_u32)),
-        ("k_is", u64p)]
-
-class VerifierOnly(ctypes.Structure):
-    _fields_ = [("constants_sigmas_cap", u64p), ("circuit_digest", c_u64 * 4)]
-
-def _sig(name, restype, *argtypes):
-    f = getattr(lib, name); f.restype = restype; f.argtypes = list(argtypes); return f
-
-_sig("b200_ctx_create", c_int, c_int, ctypes.POINTER(c_void_p))
-_sig("b200_ctx_destroy", None, c_void_p)
-_sig("b200_ctx_set_stream", c_int, c_void_p, c_void_p)
-_sig("b200_ctx_synchronize", c_int, c_void_p)
-_sig("b200_last_error", ctypes.c_char_p, c_void_p)
-_sig("b200_free", None, c_void_p)
-_sig("b200_kernel_launches", c_u64, c_void_p)
-_sig("b200_host_alloc", c_int, c_void_p, c_size_t, c_void_p)
-_sig("b200_host_free", None, c_void_p)
-_sig("b200_merkle_num_u64", c_size_t, c_u32, c_u32)
-_sig("b200_ctx_enable_timing", c_int, c_void_p, c_int)
-_sig("b200_ctx_timings", ctypes.c_char_p, c_void_p)
-_sig("b200_ntt_batch", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_int)
-_sig("b200_ntt_batch_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_int, c_void_p)
-_sig("b200_lde_commit", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_u32, c_void_p, c_void_p, c_void_p)
-_sig("b200_lde_commit_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_u32, c_void_p, c_void_p, c_void_p)
-_sig("b200_poseidon_merkle", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p, c_void_p)
-_sig("b200_poseidon_merkle_dev", c_int, c_void_p, c_void_p, c_size_t, c_u32, c_u32, c_void_p)
-_sig("b200_poseidon_permute", c_int, c_void_p, c_void_p, c_size_t)
-_sig("b200_fri_fold", c_int, c_void_p, c_void_p, c_u32, c_u32, c_void_p, c_u64, c_void_p)
-_sig("b200_msm_g1", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
-_sig("b200_msm_g1_dev", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
-_sig("b200_msm_g2", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
-_sig("b200_msm_g2_dev", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
-_sig("b200_fr_ntt", c_int, c_void_p, c_void_p, c_u32, c_int, c_int, c_void_p)
-_sig("b200_fr_ntt_dev", c_int, c_void_p, c_void_p, c_u32, c_int, c_int, c_void_p)
-_sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
-_sig("b200_verify_error", ctypes.c_char_p)
-
-EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_synchronize", "b200_last_error",
-           "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
-           "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
-           "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
-           "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev", "b200_msm_g2", "b200_msm_g2_dev", "b200_fr_ntt", "b200_fr_ntt_dev"]
-
-def _np(a):
-    a = np.ascontiguousarray(a, dtype=np.uint64)
-    return a, a.ctypes.data_as(c_void_p)
-
-class Context:
-    """One per GPU / stream (b200_ctx)."""
-    def __init__(self, device=0):
-        h = c_void_p()
-        rc = lib.b200_ctx_create(device, ctypes.byref(h))
-        if rc != 0:
-            raise B200Error(rc, "b200_ctx_create failed (no CUDA device?) -- no CPU fallback exists")
-        self.h = h
-    def close(self):
-        if self.h:
-            lib.b200_ctx_destroy(self.h); self.h = None
-    def __del__(self):
-        try: self.close()
-        except Exception: pass
-    def _chk(self, rc):
-        if rc != 0:
-            raise B200Error(rc, lib.b200_last_error(self.h).decode())
-    def set_stream(self, cuda_stream_ptr):
-        self._chk(lib.b200_ctx_set_stream(self.h, c_void_p(cuda_stream_ptr)))
-    def synchronize(self):
-        self._chk(lib.b200_ctx_synchronize(self.h))
-    def kernel_launches(self):
-        return int(lib.b200_kernel_launches(self.h))
-    def pinned_empty(self, shape, dtype=np.uint64):
-        """numpy array over page-locked memory from b200_host_alloc (freed when the array and its views are collected)."""
-        import weakref
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        p = c_void_p()
-        self._chk(lib.b200_host_alloc(self.h, nbytes, ctypes.byref(p)))
-        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(p.value)
-        weakref.finalize(buf, lib.b200_host_free, c_void_p(p.value))
-        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    def pinned_copy(self, a):
-        out = self.pinned_empty(a.shape, a.dtype); out[...] = a
-        return out
-    def enable_timing(self, on=True):
-        self._chk(lib.b200_ctx_enable_timing(self.h, int(on)))
-    def timings(self):
-        import json
-        return json.loads(lib.b200_ctx_timings(self.h).decode())
-
-    # ---- host-buffer entry points ----
-    def ntt_batch(self, values, log_n, inverse=False):
-        """values: [cols, 2^log_n] uint64 (natural order) -> transformed copy."""
-        a, p = _np(np.array(values, dtype=np.uint64, copy=True))
-        cols = a.shape[0]
-        self._chk(lib.b200_ntt_batch(self.h, p, cols, log_n, int(inverse)))
-        return a
-    def lde_commit(self, values, log_n, rate_bits=3, cap_height=4, want_lde=True, want_coeffs=True):
-        a, p = _np(values)
-        cols = a.shape[0]; n = 1 << log_n
-        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
-        lde = np.zeros((cols, n << rate_bits), dtype=np.uint64) if want_lde else None
-        co = np.zeros((cols, n), dtype=np.uint64) if want_coeffs else None
-        self._chk(lib.b200_lde_commit(self.h, p, cols, log_n, rate_bits, cap_height, cap.ctypes.data_as(c_void_p),
-                                      lde.ctypes.data_as(c_void_p) if want_lde else None,
-                                      co.ctypes.data_as(c_void_p) if want_coeffs else None))
-        return cap, lde, co
-    def poseidon_merkle(self, data, log_L, cap_height=4, want_digests=False):
-        a, p = _np(data)
-        cols = a.shape[0]
-        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
-        dg = np.zeros(lib.b200_merkle_num_u64(log_L, cap_height), dtype=np.uint64) if want_digests else None
-        self._chk(lib.b200_poseidon_merkle(self.h, p, cols, log_L, cap_height, cap.ctypes.data_as(c_void_p),
-                                           dg.ctypes.data_as(c_void_p) if want_digests else None))
-        return (cap, dg) if want_digests else cap
-    def msm_g1(self, points, scalars):
-        """points [n][8] u64 (affine x,y limbs), scalars [n][4] u64 -> (x, y) Python ints, or None for infinity."""
-        p, pp = _np(points); s, sp = _np(scalars)
-        out = np.zeros(8, dtype=np.uint64)
-        self._chk(lib.b200_msm_g1(self.h, pp, sp, p.shape[0], out.ctypes.data_as(c_void_p)))
-        x = sum(int(out[i]) << (64 * i) for i in range(4)); y = sum(int(out[4 + i]) << (64 * i) for i in range(4))
-        return None if x == 0 and y == 0 else (x, y)
-    def msm_g2(self, points, scalars):
-        """points [n][16] u64 (x.A0, x.A1, y.A0, y.A1 limbs), scalars [n][4] u64 -> ((x0, x1), (y0, y1)) or None for infinity."""
-        p, pp = _np(points); s, sp = _np(scalars)
-        out = np.zeros(16, dtype=np.uint64)
-        self._chk(lib.b200_msm_g2(self.h, pp, sp, p.shape[0], out.ctypes.data_as(c_void_p)))
-        v = [sum(int(out[4 * k + i]) << (64 * i) for i in range(4)) for k in range(4)]
-        return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
-    def fr_ntt(self, values, inverse=False, coset=False):
-        """values: [n][4] u64 canonical limbs of BN254 F_r elements (natural order) -> transformed [n][4]."""
-        a, p = _np(values)
-        n = a.shape[0]; log_n = n.bit_length() - 1
-        assert n == 1 << log_n and a.shape[1] == 4
-        out = np.zeros_like(a)
-        self._chk(lib.b200_fr_ntt(self.h, p, log_n, int(inverse), int(coset), out.ctypes.data_as(c_void_p)))
-        return out
-    def poseidon_permute(self, states):
-        a, p = _np(np.array(states, dtype=np.uint64, copy=True))
-        self._chk(lib.b200_poseidon_permute(self.h, p, a.shape[0]))
-        return a
-
-
-def common_struct(common: dict):
-    """dict with the common_data.json fields (+ "hasher": "gl" | "bn254") -> (b200_common, keep-alive objects)."""
-    c = common
-    cc = Common()
-    for k in ("num_wires", "num_routed_wires", "num_constants", "num_challenges", "degree_bits", "rate_bits", "cap_height",
-              "proof_of_work_bits", "num_query_rounds", "quotient_degree_factor", "num_partial_products",
-              "num_gate_constraints", "num_public_inputs"):
-        setattr(cc, k, c[k])
-    cc.hasher = 1 if c.get("hasher", "gl") == "bn254" else 0
-    cc.num_reduction_arity_bits = len(c["reduction_arity_bits"])
-    for i, b in enumerate(c["reduction_arity_bits"]): cc.reduction_arity_bits[i] = b
-    cc.num_gates = len(c["gates"])
-    keep = dict(ids=(ctypes.c_char_p * len(c["gates"]))(*[g.encode() for g in c["gates"]]),
-                sel=(c_u32 * len(c["gates"]))(*c["selector_indices"]),
-                gs=(c_u32 * len(c["groups"]))(*[s for s, e in c["groups"]]), ge=(c_u32 * len(c["groups"]))(*[e for s, e in c["groups"]]),
-                kis=np.array(c["k_is"], dtype=np.uint64))
-    cc.gate_ids = ctypes.cast(keep["ids"], ctypes.POINTER(ctypes.c_char_p))
-    cc.selector_indices = ctypes.cast(keep["sel"], ctypes.POINTER(c_u32))
-    cc.num_selector_groups = len(c["groups"])
-    cc.group_starts = ctypes.cast(keep["gs"], ctypes.POINTER(c_u32)); cc.group_ends = ctypes.cast(keep["ge"], ctypes.POINTER(c_u32))
-    cc.k_is = keep["kis"].ctypes.data_as(u64p)
-    return cc, keep
-
-def common_from_json(d: dict, hasher="gl"):
-    """plonky2 common_data.json (as written by near_bft_finality/src/bin/prove_block.rs:343-356) -> the dict used here."""
-    cfg, fp = d["config"], d["fri_params"]
-    return dict(num_wires=cfg["num_wires"], num_routed_wires=cfg["num_routed_wires"], num_constants=d["num_constants"],
-                num_challenges=cfg["num_challenges"], degree_bits=fp["degree_bits"], rate_bits=fp["config"]["rate_bits"],
-                cap_height=fp["config"]["cap_height"], proof_of_work_bits=fp["config"]["proof_of_work_bits"],
-                num_query_rounds=fp["config"]["num_query_rounds"], quotient_degree_factor=d["quotient_degree_factor"],
-                num_partial_products=d["num_partial_products"], num_gate_constraints=d["num_gate_constraints"],
-                num_public_inputs=d["num_public_inputs"], reduction_arity_bits=list(fp["reduction_arity_bits"]),
-                gates=list(d["gates"]), selector_indices=list(d["selectors_info"]["selector_indices"]),
-                groups=[(g["start"], g["end"]) for g in d["selectors_info"]["groups"]], k_is=list(d["k_is"]), hasher=hasher)
-
-def verify(common: dict, constants_sigmas_cap, circuit_digest, proof_bytes: bytes):
-    """CircuitData::verify: constants_sigmas_cap [2^cap_height][4] u64 words, circuit_digest 4 words.  Returns (ok, reason)."""
-    cc, keep = common_struct(common)
-    cap = np.ascontiguousarray(constants_sigmas_cap, dtype=np.uint64)
-    vo = VerifierOnly(); vo.constants_sigmas_cap = cap.ctypes.data_as(u64p)
-    for i in range(4): vo.circuit_digest[i] = int(circuit_digest[i])
-    buf = (ctypes.c_uint8 * len(proof_bytes)).from_buffer_copy(proof_bytes)
-    rc = lib.b200_verify(ctypes.byref(cc), ctypes.byref(vo), buf, len(proof_bytes))
-    return rc == 0, lib.b200_verify_error().decode()
+def __getattr__(name):
+    if name.startswith("__") or name in _SUBMODULES:      # submodules are imported by the import system, not looked up in native
+        raise AttributeError(name)
+    native = importlib.import_module(".native", __name__)
+    try:
+        return getattr(native, name)
+    except AttributeError:
+        raise AttributeError(f"module 'b200_plonky2' has no attribute {name!r}") from None

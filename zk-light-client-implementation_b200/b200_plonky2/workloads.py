@@ -19,7 +19,10 @@ def sig_circuit(degree_bits, seed=0, num_public_inputs=8):
     b.register_public_inputs(pis)
     budget = (1 << degree_bits) - b.num_rows - 8
     assert budget > 40, "degree_bits too small for the sig-shaped mix"
-    c = _mix(budget, [40, 6, 6, 8, 5, 8, 6, 6, 2, 8, 3, 2])
+    # gate histogram: a guess at the real circuit's (SURVEY App. B.1 needs a Rust box): u32 arithmetic dominates (non-native
+    # field products), SHA-512 brings interleave/uninterleave/add-many, the windowed scalar multiplication brings
+    # RandomAccessGate rows over 16-entry tables (curve_windowed_mul.rs:110-149), comparisons/range checks the reductions
+    c = _mix(budget, [40, 6, 6, 8, 5, 8, 6, 6, 2, 8, 3, 2, 6, 1])
     cb.fill_u32_arithmetic(b, rng, c[0])
     cb.fill_u32_add_many(b, rng, c[1], 2)
     cb.fill_u32_add_many(b, rng, c[2], 5)
@@ -33,6 +36,8 @@ def sig_circuit(degree_bits, seed=0, num_public_inputs=8):
     cb.fill_base_sum(b, rng, c[10])
     cs = rng.integers(0, 1 << 62, size=(c[11], 2), dtype=np.uint64)
     rc = cb.fill_constant(b, cs)
+    cb.fill_random_access(b, rng, c[12])
+    cb.fill_poseidon_chain(b, rng, c[13])
     # cross-row copy constraints: pairs of arithmetic rows share their first multiplicand via a constant row
     k = min(len(rc), len(r1))
     return b, (rc, r1, k)

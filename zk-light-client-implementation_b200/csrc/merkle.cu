@@ -6,7 +6,6 @@
 // `cols` elements costs ceil(cols/8) permutations (identity "hash" when cols <= 4); inner nodes cost one each.
 // Digest storage: level 0 (L x 4 u64) | level 1 (L/2 x 4) | ... | cap level (2^cap_height x 4).
 #include "b200_internal.h"
-#include <stdlib.h>
 #include "poseidon.cuh"
 
 #define MK_THREADS 128
@@ -165,9 +164,8 @@ __global__ void __launch_bounds__(128) k_leaves_rowmajor_quad(const u64 *__restr
 // matters (ncu on the quad form: ~28 us per tree level, ~470 dependent instructions per round per lane; here ~185: the lane
 // adds its round constant, raises its own word to the 7th power, and builds its MDS row from the other eleven words with
 // 22 shuffles and 24 wide multiply-accumulates).  A warp carries two permutations (lanes 0-11, 12-23); lanes 24-31 run the
-// same instructions on dummy data and never store.  Opt-in (B200_MERKLE_LANES=12 in the environment) until it has been
-// through the full GPU suite: the kernel-level parity tests pass with it and a recursion-sized proof spends 0.26 ms less
-// in its Merkle launches (profiles/phase_rec13_r01_v9_x12_optin.json); the prover-level run is still outstanding.
+// same instructions on dummy data and never store.  Used for every launch of <= X12_MAX_NODES permutations (a
+// recursion-sized proof spends 0.26 ms less in its Merkle launches: profiles/phase_rec13_r01_v9_x12_optin.json).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ u64 poseidon_permute_x12(u64 x, const int w, const int base) {
     const u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
@@ -214,10 +212,6 @@ __global__ void __launch_bounds__(128) k_leaves_rowmajor_x12(const u64 *__restri
     }
     if (active && w < 4) digests[4 * leaf + w] = x;
 }
-static int merkle_lanes() {        // 4 (default) or 12 (B200_MERKLE_LANES=12)
-    static const int v = [] { const char *e = getenv("B200_MERKLE_LANES"); return (e && atoi(e) == 12) ? 12 : 4; }();
-    return v;
-}
 #define X12_MAX_NODES 4096          /* above this the quad form's throughput wins */
 
 #define QUAD_MAX_NODES (size_t(148) * 16 * 32 / 4)      /* below ~19 k permutations a launch cannot fill the machine thread-per-permutation */
@@ -229,7 +223,7 @@ void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digest
 }
 void merkle_leaves_rowmajor(const u64 *data, size_t width, int log_L, u64 *digests, cudaStream_t st) {
     size_t L = size_t(1) << log_L;
-    if (width > 4 && L <= X12_MAX_NODES && merkle_lanes() == 12) k_leaves_rowmajor_x12<<<(unsigned)((L + X12_PER_BLOCK - 1) / X12_PER_BLOCK), 128, 0, st>>>(data, width, L, digests);
+    if (width > 4 && L <= X12_MAX_NODES) k_leaves_rowmajor_x12<<<(unsigned)((L + X12_PER_BLOCK - 1) / X12_PER_BLOCK), 128, 0, st>>>(data, width, L, digests);
     else if (width > 4 && L <= QUAD_MAX_NODES) k_leaves_rowmajor_quad<<<(unsigned)((4 * L + 127) / 128), 128, 0, st>>>(data, width, L, digests);
     else k_leaves_rowmajor<<<(unsigned)((L + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(data, width, L, digests);
     LAUNCHED(1);
@@ -239,7 +233,7 @@ void merkle_build(u64 *digests, int log_L, int cap_height, cudaStream_t st) {
     for (int lv = log_L; lv > cap_height; lv--) {
         size_t n = size_t(1) << lv;
         u64 *nxt = cur + 4 * n;
-        if (n / 2 <= X12_MAX_NODES && merkle_lanes() == 12) k_merkle_level_x12<<<(unsigned)((n / 2 + X12_PER_BLOCK - 1) / X12_PER_BLOCK), 128, 0, st>>>(cur, nxt, n / 2);
+        if (n / 2 <= X12_MAX_NODES) k_merkle_level_x12<<<(unsigned)((n / 2 + X12_PER_BLOCK - 1) / X12_PER_BLOCK), 128, 0, st>>>(cur, nxt, n / 2);
         else if (n / 2 <= QUAD_MAX_NODES) k_merkle_level_quad<<<(unsigned)((4 * (n / 2) + 127) / 128), 128, 0, st>>>(cur, nxt, n / 2);
         else k_merkle_level<<<(unsigned)((n / 2 + MK_THREADS - 1) / MK_THREADS), MK_THREADS, 0, st>>>(cur, nxt, n / 2);
         LAUNCHED(1);

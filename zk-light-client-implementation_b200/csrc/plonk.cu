@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(128) k_chunk_quotients(const u64 *__restrict__
 // exclusive multiplicative scan over rows, 1024 elements per block
 #define SCAN_T 256
 #define SCAN_E 4
-__global__ void __launch_bounds__(SCAN_T) k_scan_local(const u64 *__restrict__ in, u64 *__restrict__ excl, u64 *__restrict__ block_tot, size_t n) {
+// `in` and `excl` may alias (the prover scans the row products in place): no __restrict__ on either
+__global__ void __launch_bounds__(SCAN_T) k_scan_local(const u64 *in, u64 *excl, u64 *__restrict__ block_tot, size_t n) {
     __shared__ u64 sh[SCAN_T];
     size_t c = blockIdx.y;
     size_t base = (size_t)blockIdx.x * SCAN_T * SCAN_E + threadIdx.x * SCAN_E;

@@ -19,9 +19,14 @@ struct QuotientArgs {
     u64 n_inv;                                   // 1/n
 };
 
+// scratch words launch_partial_products needs: chunk quotients nch*(npp+1)*n, row products nch*n, scan block totals nch*ceil(n/1024)
+static inline size_t partial_products_scratch_u64(int log_n, u32 npp, u32 nch) {
+    const size_t n = size_t(1) << log_n;
+    return (size_t)nch * (npp + 2) * n + (size_t)nch * ((n + 1023) / 1024) + 64;
+}
 void launch_partial_products(const u64 *d_wires, const u64 *d_sigmas, const u64 *d_kis, int log_n, u32 num_routed, u32 npp, u32 qdf,
                              u32 num_challenges, const u64 *betas, const u64 *gammas, const u64 *tw_fwd,
-                             u64 *d_zs_pp /*[nch*(1+npp)][n]*/, u64 *d_scratch /* >= nch*(npp+2)*n + 4096 u64 */, u64 *d_final_prod /*[nch]*/,
+                             u64 *d_zs_pp /*[nch*(1+npp)][n]*/, u64 *d_scratch /* partial_products_scratch_u64() words */, u64 *d_final_prod /*[nch]*/,
                              cudaStream_t st);
 void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, cudaStream_t st);
 // big[ci][.] (size N, br order, coefficients of the coset-shifted quotient) -> chunk polys coeffs_br[ci*qdf + m][n]

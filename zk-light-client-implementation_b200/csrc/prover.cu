@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "host_common.h"
+#include "vanishing.h"
 
 // ------------------------------------------------------------------------------------------------
 struct b200_circuit {
@@ -30,7 +31,7 @@ struct b200_circuit {
         qdf, npp, num_gate_constraints, num_pi, num_selectors, hasher;
     std::vector<u32> arity_bits;
     std::vector<GateDesc> gates;
-    std::vector<u64> k_is;
+    std::vector<u64> k_is, extra;       // extra: per-gate constant tables (barycentric weights), host copy
     DevBuf d_gates, d_extra, d_kis;
     DevBuf cs_coeffs, cs_lde, cs_digests, sigma_values;
     u64 digest[4];
@@ -97,15 +98,6 @@ __global__ void k_copy_descs(const CopyDesc *__restrict__ d, u64 *__restrict__ d
     for (u32 i = threadIdx.x; i < c.count; i += blockDim.x) dst[c.dst_off + i] = c.src[(size_t)i * c.stride];
 }
 
-static void dump_dev(const char *dir, const char *name, const void *d, size_t bytes, cudaStream_t st) {
-    if (!dir) return;
-    std::vector<uint8_t> h(bytes);
-    CUDA_TRY(cudaMemcpyAsync(h.data(), d, bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    std::string p = std::string(dir) + "/" + name;
-    FILE *f = fopen(p.c_str(), "wb"); if (f) { fwrite(h.data(), 1, bytes, f); fclose(f); }
-}
-
 static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in, bool wires_on_device, const u64 *pis, size_t n_pis,
                       u64 pow_hint, uint8_t **proof_out, size_t *proof_len) {
     cudaStream_t st = ctx->stream;
@@ -119,16 +111,16 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     const u32 nzp = nch * (1 + npp), nq = nch * qdf;
     const size_t capw = size_t(4) << chh, ncap = size_t(1) << chh;
     const int HS = (int)k->hasher;
-    const char *dbg = getenv("B200_DEBUG_DUMP");
     if (n_pis != k->num_pi) throw ApiErr{B200_ERR_BAD_ARG, "b200_prove: wrong number of public inputs"};
     ntt_tables_ensure(ctx->tw, Llog, st);
 
     // ---- arena layout ----
     const size_t dig_u64 = merkle_num_u64(Llog, chh);
+    const size_t pp_scratch_u64 = partial_products_scratch_u64(nlog, npp, nch);
     size_t need = 0;
     auto rnd = [](size_t u) { return (u * 8 + 255) & ~size_t(255); };
     need += (wires_on_device ? 0 : rnd((size_t)W * n)) + rnd((size_t)W * n) + rnd((size_t)W * N) + rnd(dig_u64);      // wires
-    need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd((size_t)nch * (npp + 2) * n + 8192) + rnd(8);   // zs
+    need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd(pp_scratch_u64) + rnd(8);   // zs
     need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64);                        // quotient
     need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)); // openings tables
     need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
@@ -139,6 +131,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     u64 pi_hash[4]; poseidon_hash_no_pad_host(pis, n_pis, pi_hash);
     const u64 *d_wires;
     if (wires_on_device) d_wires = wires_in;
+    struct CopyDrain { cudaStream_t s = nullptr; ~CopyDrain() { if (s) cudaStreamSynchronize(s); } } drain;
     u64 *w_coeffs = A.take((size_t)W * n), *w_lde = A.take((size_t)W * N), *w_dig = A.take(dig_u64);
     if (wires_on_device) commit_values(ctx, d_wires = wires_in, W, nlog, rb, chh, w_coeffs, w_lde, w_dig, HS);
     else {
@@ -147,27 +140,31 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         u64 *t = A.take((size_t)W * n); d_wires = t;
         if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         const u32 nchunks = W >= 32 ? (u32)std::min<size_t>(6, std::max<size_t>(1, ((size_t)W * n) >> 19)) : 1;   // >= 2^19 words per chunk: small proofs are launch-bound
-        std::vector<cudaEvent_t> evs(nchunks);
-        cudaEvent_t start_ev; CUDA_TRY(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(start_ev, st)); CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, start_ev, 0));   // arena reuse ordering
+        // RAII: the events die and the copy stream is drained on every exit path (the caller's witness buffer must not
+        // have an H2D copy in flight once b200_prove returns, error or not)
+        struct Ev { cudaEvent_t e = nullptr; Ev() { CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); } ~Ev() { if (e) cudaEventDestroy(e); }
+                    Ev(const Ev &) = delete; Ev &operator=(const Ev &) = delete; };
+        drain.s = ctx->copy_stream;
+        std::vector<std::unique_ptr<Ev>> evs;
+        for (u32 c = 0; c < nchunks; c++) evs.emplace_back(new Ev());
+        Ev start_ev;
+        CUDA_TRY(cudaEventRecord(start_ev.e, st)); CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, start_ev.e, 0));   // arena reuse ordering
         for (u32 c = 0; c < nchunks; c++) {
             size_t c0 = (size_t)W * c / nchunks, c1 = (size_t)W * (c + 1) / nchunks;
             CUDA_TRY(cudaMemcpyAsync(t + c0 * n, wires_in + c0 * n, (c1 - c0) * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CUDA_TRY(cudaEventCreateWithFlags(&evs[c], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventRecord(evs[c], ctx->copy_stream));
+            CUDA_TRY(cudaEventRecord(evs[c]->e, ctx->copy_stream));
         }
         for (u32 c = 0; c < nchunks; c++) {
             size_t c0 = (size_t)W * c / nchunks, c1 = (size_t)W * (c + 1) / nchunks;
-            CUDA_TRY(cudaStreamWaitEvent(st, evs[c], 0));
+            CUDA_TRY(cudaStreamWaitEvent(st, evs[c]->e, 0));
             commit_values_lde_only(ctx, t + c0 * n, c1 - c0, nlog, rb, w_coeffs + c0 * n, w_lde + c0 * N);
         }
         commit_hash_only(ctx, w_lde, W, nlog, rb, chh, w_dig, HS);
-        for (auto e : evs) cudaEventDestroy(e);
-        cudaEventDestroy(start_ev);
     }
     std::vector<u64> cap_w(capw), cap_z(capw), cap_q(capw);
     S.d2h(cap_w.data(), w_dig + dig_u64 - capw, capw * 8);
     S.sync();
+    drain.s = nullptr;          // the compute stream waited on every chunk's event: the witness copies are complete
 
     Challenger ch;
     ch.observe_hash(k->digest, HS); ch.observe_n(pi_hash, 4); ch.observe_cap(cap_w.data(), ncap, HS);
@@ -177,7 +174,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
 
     // ---- partial products + Z ----
     u64 *zs_vals = A.take((size_t)nzp * n), *zs_coeffs = A.take((size_t)nzp * n), *zs_lde = A.take((size_t)nzp * N), *zs_dig = A.take(dig_u64);
-    u64 *pp_scratch = A.take((size_t)nch * (npp + 2) * n + 8192), *d_final_prod = A.take(8);
+    u64 *pp_scratch = A.take(pp_scratch_u64), *d_final_prod = A.take(8);
     { PhaseTimer t(ctx, "partial_products");
     launch_partial_products(d_wires, k->sigma_values.u(), k->d_kis.u(), nlog, R, npp, qdf, nch, betas, gammas, ctx->tw.fwd, zs_vals, pp_scratch, d_final_prod, st); }
     commit_values(ctx, zs_vals, nzp, nlog, rb, chh, zs_coeffs, zs_lde, zs_dig, HS);
@@ -186,7 +183,6 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     S.d2h(final_prod, d_final_prod, nch * 8);
     S.sync();
     for (u32 i = 0; i < nch; i++) if (final_prod[i] != 1) throw ApiErr{B200_ERR_UNSATISFIED, "permutation argument: grand product != 1 (copy constraints violated)"};
-    if (dbg) dump_dev(dbg, "zs_pp_values.bin", zs_vals, (size_t)nzp * n * 8, st);
     ch.observe_cap(cap_z.data(), ncap, HS);
     for (u32 i = 0; i < nch; i++) alphas[i] = ch.get();
 
@@ -225,7 +221,6 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     commit_coeffs(ctx, q_coeffs, nq, nlog, rb, chh, q_lde, q_dig, HS);
     S.d2h(cap_q.data(), q_dig + dig_u64 - capw, capw * 8);
     S.sync();
-    if (dbg) dump_dev(dbg, "quotient_coeffs_br.bin", q_coeffs, (size_t)nq * n * 8, st);
     ch.observe_cap(cap_q.data(), ncap, HS);
     gl2 zeta = ch.get_ext();
     if (gl2_eq(gl2_pow(zeta, (u64)n), gl2_make(1, 0))) throw ApiErr{B200_ERR_UNSATISFIED, "opening point zeta lies in the subgroup"};
@@ -252,6 +247,14 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     std::vector<gl2> open(total_polys + nch);
     S.d2h(open.data(), d_open, open.size() * sizeof(gl2));
     S.sync();
+    {   // the prover checks its own openings: a violated GATE constraint leaves every committed polynomial low-degree (the
+        // quotient is interpolated from its coset values), so FRI cannot see it -- only the identity at zeta can
+        const gl2 *o = open.data();
+        VanishingInput vi{W, R, NC, nch, qdf, npp, k->num_gate_constraints, k->num_selectors, nlog, k->k_is.data(), &k->gates, k->extra.data(), pi_hash,
+                          betas, gammas, alphas, zeta, o, o + NC, o + NC + R, o + NC + R + W, o + total_polys, o + NC + R + W + nch, o + NC + R + W + nzp};
+        if (const char *why = vanishing_identity_at_zeta(vi))
+            throw ApiErr{B200_ERR_UNSATISFIED, std::string("witness does not satisfy the circuit: ") + why + " (a gate constraint is violated)"};
+    }
     for (size_t i = 0; i < total_polys; i++) ch.observe_ext(open[i]);
     for (u32 i = 0; i < nch; i++) ch.observe_ext(open[total_polys + i]);
 
@@ -273,7 +276,6 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         fa.alpha_nch = gl2_pow(fri_alpha, nch); fa.tw_fwd = ctx->tw.fwd; fa.log_N = Llog; fa.out = fri_a;
         { PhaseTimer t(ctx, "fri_combine"); launch_fri_combine(fa, st); }
     }
-    if (dbg) dump_dev(dbg, "fri_values0.bin", fri_a, N * 16, st);
     // commit phase: layers[l] = values (device, kept for the query phase), digests
     struct Layer { gl2 *vals; u64 *dig; int log_len, log_leaves; size_t dig_u64; };
     std::vector<Layer> layers;
@@ -408,16 +410,6 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     put_u64(out, (u64)n_pis);
     put_words(out, pis, n_pis);
 
-    if (dbg) {
-        std::string p = std::string(dbg) + "/challenges.txt";
-        FILE *f = fopen(p.c_str(), "w");
-        if (f) {
-            fprintf(f, "betas %llu %llu\ngammas %llu %llu\nalphas %llu %llu\nzeta %llu %llu\nfri_alpha %llu %llu\n", (unsigned long long)betas[0], (unsigned long long)betas[1],
-                    (unsigned long long)gammas[0], (unsigned long long)gammas[1], (unsigned long long)alphas[0], (unsigned long long)alphas[1],
-                    (unsigned long long)zeta.a, (unsigned long long)zeta.b, (unsigned long long)fri_alpha.a, (unsigned long long)fri_alpha.b);
-            fclose(f);
-        }
-    }
     uint8_t *buf = (uint8_t *)malloc(out.size());
     if (!buf) throw ApiErr{B200_ERR_OOM, "host allocation failed"};
     memcpy(buf, out.data(), out.size());
@@ -443,7 +435,9 @@ int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_
     *out = nullptr;
     if (c->hasher > 1) throw ApiErr{B200_ERR_UNSUPPORTED, "hasher must be 0 (PoseidonGoldilocksConfig) or 1 (PoseidonBN128GoldilocksConfig)"};
     if (c->num_challenges == 0 || c->num_challenges > MAX_CHALLENGES) throw ApiErr{B200_ERR_UNSUPPORTED, "num_challenges must be 1 or 2"};
+    if (c->rate_bits == 0 || c->rate_bits > 4) throw ApiErr{B200_ERR_UNSUPPORTED, "rate_bits must be in 1..4"};     // QuotientArgs::zh_ev[16]
     if (c->quotient_degree_factor != (1u << c->rate_bits)) throw ApiErr{B200_ERR_UNSUPPORTED, "quotient_degree_factor must equal 2^rate_bits"};
+    if (c->num_reduction_arity_bits > 16) throw ApiErr{B200_ERR_BAD_ARG, "too many FRI reductions"};
     if (c->degree_bits < 2 || c->degree_bits + c->rate_bits > 28) throw ApiErr{B200_ERR_BAD_ARG, "degree_bits out of range"};
     if (c->num_routed_wires > c->num_wires || c->num_partial_products + 1 > 16 ||
         (c->num_partial_products + 1) * c->quotient_degree_factor < c->num_routed_wires)
@@ -463,7 +457,7 @@ int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_
         k->arity_bits.push_back(ab); bits_left -= (int)ab;
     }
     if (bits_left < (int)c->rate_bits) throw ApiErr{B200_ERR_BAD_ARG, "too many FRI reductions"};
-    std::vector<u64> extra;
+    std::vector<u64> &extra = k->extra;
     for (u32 i = 0; i < c->num_gates; i++) {
         GateDesc g;
         if (!c->gate_ids[i] || !parse_gate(c->gate_ids[i], g, extra)) { std::string m = "unsupported gate id: "; m += c->gate_ids[i] ? c->gate_ids[i] : "(null)"; throw ApiErr{B200_ERR_UNSUPPORTED, m}; }

@@ -7,16 +7,8 @@
 #include "../../include/b200_plonky2.h"
 #include "host_common.h"
 #include "verify_gates.h"
+#include "vanishing.h"
 #include <string>
-
-struct X2 {            // F_p^2 with operators, for the generic gate evaluators
-    gl2 v;
-    static X2 from(u64 x) { X2 r; r.v = gl2_make(x % GL_P, 0); return r; }
-    X2 operator+(const X2 &o) const { X2 r; r.v = gl2_add(v, o.v); return r; }
-    X2 operator-(const X2 &o) const { X2 r; r.v = gl2_sub(v, o.v); return r; }
-    X2 operator*(const X2 &o) const { X2 r; r.v = gl2_mul(v, o.v); return r; }
-};
-static X2 mk(gl2 v) { X2 r; r.v = v; return r; }
 
 static thread_local std::string g_verify_err;
 struct VerifyFail { std::string msg; };
@@ -63,6 +55,11 @@ static gl2 ext_pow(gl2 a, u64 e) { return gl2_pow(a, e); }
 static int verify_impl(const b200_common *c, const b200_verifier_only *vo, const uint8_t *proof, size_t len) {
     if (!c || !vo || !proof || !vo->constants_sigmas_cap) VFAIL("null argument");
     if (c->hasher > 1 || c->num_challenges == 0 || c->num_challenges > 4) VFAIL("unsupported config");
+    if (c->degree_bits == 0 || c->degree_bits > 32 || c->rate_bits == 0 || c->rate_bits > 8 || c->cap_height > c->degree_bits + c->rate_bits ||
+        c->proof_of_work_bits == 0 || c->proof_of_work_bits > 32 || c->num_reduction_arity_bits > 16 || c->num_query_rounds > 4096 ||
+        c->quotient_degree_factor == 0 || c->num_routed_wires > c->num_wires || c->num_gates > 4096)
+        VFAIL("common data out of range");
+    for (u32 i = 0; i < c->num_reduction_arity_bits; i++) if (c->reduction_arity_bits[i] == 0 || c->reduction_arity_bits[i] > 8) VFAIL("reduction arity bits out of range");
     const int HS = (int)c->hasher;
     const u32 W = c->num_wires, R = c->num_routed_wires, NC = c->num_constants, nch = c->num_challenges, qdf = c->quotient_degree_factor, npp = c->num_partial_products;
     const int nlog = (int)c->degree_bits, rb = (int)c->rate_bits, chh = (int)c->cap_height, Llog = nlog + rb;
@@ -125,48 +122,12 @@ static int verify_impl(const b200_common *c, const b200_verifier_only *vo, const
     u64 pow_response = ch.get();
     std::vector<u64> qidx(c->num_query_rounds); for (auto &q : qidx) q = ch.get();
     // ---- vanishing polynomial identity at zeta (plonk.go:121-250) ----
-    const size_t n = size_t(1) << nlog;
-    gl2 zeta_pow_n = zeta; for (int i = 0; i < nlog; i++) zeta_pow_n = gl2_mul(zeta_pow_n, zeta_pow_n);
     {
-        std::vector<X2> consts(NC), wires(W);
-        for (u32 i = 0; i < NC; i++) consts[i] = mk(o_const[i]);
-        for (u32 i = 0; i < W; i++) wires[i] = mk(o_wires[i]);
-        std::vector<X2> gate_terms(c->num_gate_constraints, X2::from(0));
-        const u32 nsel = c->num_selector_groups;
-        for (auto &g : gates) {
-            X2 sel = consts[g.selector_index], filt = X2::from(1);
-            for (u32 r = g.group_start; r < g.group_end; r++) if (r != g.row) filt = filt * (X2::from(r) - sel);
-            if (nsel > 1) filt = filt * (X2::from(0xFFFFFFFFULL) - sel);
-            std::vector<X2> cons;
-            if (!eval_gate_generic<X2>(g, consts.data() + nsel, wires.data(), pi_hash, extra.data(), cons)) VFAIL("gate evaluation failed");
-            if (cons.size() != g.num_constraints || cons.size() > c->num_gate_constraints) VFAIL("gate constraint count mismatch");
-            for (size_t i = 0; i < cons.size(); i++) gate_terms[i] = gate_terms[i] + cons[i] * filt;
-        }
-        gl2 one = gl2_make(1, 0);
-        gl2 l0 = gl2_mul(gl2_sub(zeta_pow_n, one), gl2_inv(gl2_scale(gl2_sub(zeta, one), (u64)n % GL_P)));
-        std::vector<gl2> terms;
-        for (u32 i = 0; i < nch; i++) terms.push_back(gl2_mul(l0, gl2_sub(o_zs[i], one)));
-        for (u32 i = 0; i < nch; i++) {
-            std::vector<gl2> accs; accs.push_back(o_zs[i]); for (u32 k = 0; k < npp; k++) accs.push_back(o_pp[i * npp + k]); accs.push_back(o_zs_next[i]);
-            for (u32 k = 0; k <= npp; k++) {
-                gl2 num = one, den = one;
-                for (u32 j = k * qdf; j < (k + 1) * qdf && j < R; j++) {
-                    gl2 wg = gl2_add_base(o_wires[j], gammas[i]);
-                    num = gl2_mul(num, gl2_add(wg, gl2_scale(zeta, gl_mul(c->k_is[j], betas[i]))));
-                    den = gl2_mul(den, gl2_add(wg, gl2_scale(o_sig[j], betas[i])));
-                }
-                terms.push_back(gl2_sub(gl2_mul(accs[k], num), gl2_mul(accs[k + 1], den)));
-            }
-        }
-        for (auto &t : gate_terms) terms.push_back(t.v);
-        gl2 zh = gl2_sub(zeta_pow_n, one);
-        for (u32 i = 0; i < nch; i++) {
-            gl2 acc = gl2_make(0, 0);
-            for (size_t t = terms.size(); t-- > 0;) acc = gl2_add(gl2_scale(acc, alphas[i]), terms[t]);
-            gl2 q = gl2_make(0, 0);
-            for (u32 k = qdf; k-- > 0;) q = gl2_add(gl2_mul(q, zeta_pow_n), o_quot[i * qdf + k]);
-            if (!gl2_eq(acc, gl2_mul(zh, q))) VFAIL("vanishing polynomial identity failed");
-        }
+        VanishingInput vi{c->num_wires, c->num_routed_wires, c->num_constants, nch, qdf, npp, c->num_gate_constraints, c->num_selector_groups, nlog,
+                          c->k_is, &gates, extra.data(), pi_hash, betas.data(), gammas.data(), alphas.data(), zeta,
+                          o_const.data(), o_sig.data(), o_wires.data(), o_zs.data(), o_zs_next.data(), o_pp.data(), o_quot.data()};
+        const char *why = vanishing_identity_at_zeta(vi);
+        if (why) VFAIL(why);
     }
     // ---- FRI (fri.go:63-548) ----
     if (pow_response >> (64 - c->proof_of_work_bits)) VFAIL("proof of work failed");
