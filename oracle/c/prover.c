@@ -16,6 +16,9 @@
 #include <string.h>
 #include <stdio.h>
 #include <omp.h>
+/* phase wall clock to stderr when ORC_TIMING is set (test infrastructure only) */
+static double orc_t0_; static int orc_timing_ = -1;
+#define ORC_TICK(name) do { if (orc_timing_ < 0) orc_timing_ = getenv("ORC_TIMING") != NULL; if (orc_timing_) { double t_ = omp_get_wtime(); fprintf(stderr, "[orc] %-22s %8.3f s\n", name, t_ - orc_t0_); orc_t0_ = t_; } } while (0)
 
 void orc_poseidon_permute(u64 s[12]);
 void orc_hash_no_pad(const u64 *in, size_t n, u64 out[4]);
@@ -136,10 +139,12 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
     const size_t capn = 4ULL << ch_h;
     if (qdf != (1u << rb)) return -5;
 
+    orc_t0_ = omp_get_wtime();
     u64 pi_hash[4]; orc_hash_no_pad(pis, c->num_pi, pi_hash);
     const int HS = (int)c->hasher; const size_t ncaph = 1ULL << ch_h;
     batch wires; batch_from_values(&wires, wires_values, W, nlog, rb, ch_h, HS);
 
+    ORC_TICK("wires commit");
     chal ch; ch_init(&ch);
     ch_observe_hash(&ch, k->digest, HS); ch_observe_n(&ch, pi_hash, 4); ch_observe_cap(&ch, batch_cap(&wires), ncaph, HS);
     u64 betas[4], gammas[4], alphas[4];
@@ -183,7 +188,9 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         if (z != 1) { fprintf(stderr, "orc_prove: permutation product != 1 (copy constraints violated)\n"); }
     }
     if (dbg && dbg->zs_pp_values) memcpy(dbg->zs_pp_values, zs_pp, (size_t)nzp * n * 8);
+    ORC_TICK("partial products");
     batch zsb; batch_from_values(&zsb, zs_pp, nzp, nlog, rb, ch_h, HS);
+    ORC_TICK("zs commit");
     ch_observe_cap(&ch, batch_cap(&zsb), ncaph, HS);
     for (uint32_t i = 0; i < nch; i++) alphas[i] = ch_get(&ch);
 
@@ -240,6 +247,7 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         (void)bad;
         free(points);
     }
+    ORC_TICK("quotient eval");
     /* coset_ifft(shift): ifft then divide coefficient k by shift^k */
     batch quot; quot.coeffs = (u64 *)malloc((size_t)nch * qdf * n * 8);
     {
@@ -253,7 +261,9 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
     }
     free(qvals);
     if (dbg && dbg->quotient_coeffs) memcpy(dbg->quotient_coeffs, quot.coeffs, (size_t)nch * qdf * n * 8);
+    ORC_TICK("quotient ifft");
     batch_from_coeffs(&quot, (size_t)nch * qdf, nlog, rb, ch_h, HS);
+    ORC_TICK("quotient commit");
     ch_observe_cap(&ch, batch_cap(&quot), ncaph, HS);
     e2 zeta = ch_get_ext(&ch);
 
@@ -280,6 +290,7 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
             open_next[ci] = acc;
         }
     }
+    ORC_TICK("openings");
     /* observe openings: constants, sigmas, wires, zs, partial products, quotient (== oracle order), then zs_next */
     for (size_t i = 0; i < total_polys; i++) { ch_observe(&ch, open_zeta[i].a); ch_observe(&ch, open_zeta[i].b); }
     for (uint32_t i = 0; i < nch; i++) { ch_observe(&ch, open_next[i].a); ch_observe(&ch, open_next[i].b); }
@@ -315,6 +326,7 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
             free(comp); free(quo);
         }
     }
+    ORC_TICK("fri batch poly");
     /* lde + coset fft (shift g) of the extension-field polynomial, component-wise */
     size_t cur_len = N;
     e2 *coeffs = (e2 *)calloc(N, sizeof(e2));
@@ -374,6 +386,7 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         cur_len = new_len; cur_log -= ab;
         COSET_FFT(cur_log);
     }
+    ORC_TICK("fri commit phase");
     /* final poly: truncate to len >> rate_bits (the removed coefficients must be zero) */
     size_t fin_len = cur_len >> rb;
     for (size_t i = fin_len; i < cur_len; i++) if (coeffs[i].a || coeffs[i].b) { fprintf(stderr, "orc_prove: final poly has high-degree terms (quotient not low degree)\n"); break; }
@@ -402,6 +415,7 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
         u64 resp = ch_get(&ch);
         if (resp >> (64 - c->pow_bits)) return -3;
     }
+    ORC_TICK("pow");
     /* query rounds */
     wbuf qb = { 0, 0, 0 };
     for (uint32_t q = 0; q < c->num_queries; q++) {
@@ -425,6 +439,7 @@ int orc_prove(const orc_circuit *k, const u64 *wires_values, const u64 *pis, u64
     wb_u64(&out, c->num_pi);
     for (uint32_t i = 0; i < c->num_pi; i++) wb_u64(&out, pis[i]);
 
+    ORC_TICK("queries+serialize");
     if (dbg) {
         memcpy(dbg->betas, betas, sizeof betas); memcpy(dbg->gammas, gammas, sizeof gammas); memcpy(dbg->alphas, alphas, sizeof alphas);
         dbg->zeta[0] = zeta.a; dbg->zeta[1] = zeta.b; dbg->fri_alpha[0] = fri_alpha.a; dbg->fri_alpha[1] = fri_alpha.b;

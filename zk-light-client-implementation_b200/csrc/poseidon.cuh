@@ -248,48 +248,224 @@ GL_HD void poseidon_two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
     out[0] = s[0]; out[1] = s[1]; out[2] = s[2]; out[3] = s[3];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Limb-resident permutation (round 2).  ncu on the round-1 kernel: 33.2 k thread-instructions per permutation at 74 % of
+// the issue slots -- only fewer instructions help.  Where they went: every MDS layer re-split its 12 inputs into 22-bit
+// limbs and recombined + reduced its 12 outputs to 64 bits (~25 of ~50 instructions per word per layer), although in the
+// 22 partial rounds eleven of the twelve words go from one linear layer straight into the next.  Here a word stays a limb
+// triple (21 | 21 | 22 bits) between layers:
+//   * partial rounds: words 1..11 are only carry-normalised (10 instructions: pl_normalise) -- the MDS grows a limb by
+//     < 2^8.05, so limbs < 2^22 keep every intermediate of the shift/add transform < 2^31 (L1 norm of every intermediate
+//     form <= 256, checked in tests/test_host_emulations.py) -- and their round constants are not added at all: they are
+//     pushed forward through the linear layers into one scalar per round for word 0 and a correction of round 26's
+//     constants (csrc/tools/gen_poseidon_limb_tables.py; the forward form of plonky2's FAST_PARTIAL_* constant pushing);
+//   * word 0 of a partial round and all words of a full round are recombined to 64 bits for the S-box with a carry
+//     chain that folds the top bits once (pl_recombine, 2^64 == 2^32 - 1), constants are added limb-wise before it;
+//   * the 64x64 product is four independent IMAD.WIDE plus a six-instruction carry chain (gl_mul_nc4).
+// Every carry step adds HB = 512 to the value it normalises (limb 0 += HB - h keeps limbs non-negative); the generated
+// constants absorb it.  Same permutation, bit-exact (host emulation test + GPU parity tests).
+// ---------------------------------------------------------------------------------------------------------------
+#include "poseidon_limb_tables.cuh"
+struct pl_c4 { u32 a, b, c, pad; };
+static const pl_c4 h_POSEIDON_L_RC[96] = POSEIDON_L_RC_INIT;
+static const pl_c4 h_POSEIDON_L_PK[22] = POSEIDON_L_PK_INIT;
 #ifdef __CUDACC__
-// ---------------------------------------------------------------------------------------------------------------
-// Compact device permutation.  ncu on the first version (state in registers, everything unrolled: ~15k SASS
-// instructions per kernel) showed issue-slot utilisation of 35 % with "no_instruction" as the dominant stall: the
-// instruction stream did not fit the SM's instruction caches.  This version keeps the 12-word state in SHARED memory
-// (element-major: word i of thread t at st[i * stride], conflict-free) so that the S-box layer is a rolled loop and the
-// 30 rounds share one copy of the (unrolled, shift/add-only) MDS code: ~1.3k instructions total.  Partial rounds use
-// the textbook form (S-box on word 0, all 12 round constants, full MDS) because with the multiplier-free MDS that is
-// cheaper than the "fast" sparse-matrix form (23 modmuls) and needs no extra tables.  Same permutation, bit-exact.
-// ---------------------------------------------------------------------------------------------------------------
-static __device__ __noinline__ void poseidon_permute_smem(u64 *st, const int stride) {
-    for (int r = 0; r < 30; r++) {
-        const bool full = (r < 4) || (r >= 26);
-        const u64 *rc = d_POSEIDON_RC + 12 * r;
-        u64 s[12];
-        if (full) {
-#pragma unroll 2
-            for (int i = 0; i < 12; i++) {
-                u64 c = rc[i];
-                u64 x = st[i * stride] + c;
-                if (x < c) x += GL_EPS;
-                st[i * stride] = poseidon_sbox(x);
-            }
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = st[i * stride];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                u64 c = rc[i];
-                u64 x = st[i * stride] + c;
-                if (x < c) x += GL_EPS;
-                s[i] = x;
-            }
-            s[0] = poseidon_sbox(s[0]);
-        }
-        poseidon_mds(s);
-#pragma unroll
-        for (int i = 0; i < 12; i++) st[i * stride] = s[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) st[i * stride] = gl_canon(st[i * stride]);
+__constant__ pl_c4 d_POSEIDON_L_RC[96] = POSEIDON_L_RC_INIT;
+__constant__ pl_c4 d_POSEIDON_L_PK[22] = POSEIDON_L_PK_INIT;
+#endif
+#define PL_M21 0x1FFFFFu
+#define PL_M22 0x3FFFFFu
+
+// (a * b) mod p, any 64-bit inputs, result in [0, 2^64).  Device: 4 IMAD.WIDE.U32 without shifted addends (a shifted
+// addend needs its 64-bit register pair rebuilt: two extra moves per product in the SASS of gl_mul_wide).
+GL_HD u64 gl_mul_nc4(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u64 p00, p01, p10, p11;\n\t"
+        ".reg .u32 x0, x1, x2, x3, a0, a1, b0, b1, l01, h01, l10, h10, l11, h11, h00, m0, m1, m2, t0l, t0h, bm, t1l, t1h, cm;\n\t"
+        "mov.b64 {a0, a1}, %2;\n\t"
+        "mov.b64 {b0, b1}, %3;\n\t"
+        "mul.wide.u32 p00, a0, b0;\n\t"
+        "mul.wide.u32 p01, a0, b1;\n\t"
+        "mul.wide.u32 p10, a1, b0;\n\t"
+        "mul.wide.u32 p11, a1, b1;\n\t"
+        "mov.b64 {x0, h00}, p00;\n\t"
+        "mov.b64 {l01, h01}, p01;\n\t"
+        "mov.b64 {l10, h10}, p10;\n\t"
+        "mov.b64 {l11, h11}, p11;\n\t"
+        "add.cc.u32 m0, l01, l10;\n\t"          // mid = p01 + p10 (65 bits: m2:m1:m0)
+        "addc.cc.u32 m1, h01, h10;\n\t"
+        "addc.u32 m2, 0, 0;\n\t"
+        "add.cc.u32 x1, h00, m0;\n\t"           // product = x3:x2:x1:x0
+        "addc.cc.u32 x2, l11, m1;\n\t"
+        "addc.u32 x3, h11, m2;\n\t"
+        // reduce: x0 + x1*2^32 + x2*(2^32 - 1) - x3
+        "sub.cc.u32 t0l, x0, x3;\n\t"
+        "subc.cc.u32 t0h, x1, 0;\n\t"
+        "subc.u32 bm, 0, 0;\n\t"                // borrow mask
+        "sub.cc.u32 t0l, t0l, bm;\n\t"          // -= EPS on borrow
+        "subc.u32 t0h, t0h, 0;\n\t"
+        "sub.cc.u32 t1l, 0, x2;\n\t"            // t1 = (x2 << 32) - x2
+        "subc.u32 t1h, x2, 0;\n\t"
+        "add.cc.u32 %0, t0l, t1l;\n\t"
+        "addc.cc.u32 %1, t0h, t1h;\n\t"
+        "addc.u32 cm, 0, 0;\n\t"
+        "neg.s32 cm, cm;\n\t"
+        "add.cc.u32 %0, %0, cm;\n\t"            // += EPS on carry
+        "addc.u32 %1, %1, 0;\n\t"
+        "}" : "=&r"(r0), "=&r"(r1) : "l"(a), "l"(b));
+    return ((u64)r1 << 32) | r0;
+#else
+    return gl_mul_nc(a, b);
+#endif
 }
+// a^2 mod p with three wide multiplies (a0*a1 counted twice)
+GL_HD u64 gl_sqr_nc4(u64 a) {
+#ifdef __CUDA_ARCH__
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u64 p00, p01, p11;\n\t"
+        ".reg .u32 x0, x1, x2, x3, a0, a1, l01, h01, l11, h11, h00, m0, m1, m2, t0l, t0h, bm, t1l, t1h, cm;\n\t"
+        "mov.b64 {a0, a1}, %2;\n\t"
+        "mul.wide.u32 p00, a0, a0;\n\t"
+        "mul.wide.u32 p01, a0, a1;\n\t"
+        "mul.wide.u32 p11, a1, a1;\n\t"
+        "mov.b64 {x0, h00}, p00;\n\t"
+        "mov.b64 {l01, h01}, p01;\n\t"
+        "mov.b64 {l11, h11}, p11;\n\t"
+        "shl.b32 m0, l01, 1;\n\t"                // mid = 2 * p01
+        "shf.l.clamp.b32 m1, l01, h01, 1;\n\t"
+        "shr.b32 m2, h01, 31;\n\t"
+        "add.cc.u32 x1, h00, m0;\n\t"
+        "addc.cc.u32 x2, l11, m1;\n\t"
+        "addc.u32 x3, h11, m2;\n\t"
+        "sub.cc.u32 t0l, x0, x3;\n\t"
+        "subc.cc.u32 t0h, x1, 0;\n\t"
+        "subc.u32 bm, 0, 0;\n\t"
+        "sub.cc.u32 t0l, t0l, bm;\n\t"
+        "subc.u32 t0h, t0h, 0;\n\t"
+        "sub.cc.u32 t1l, 0, x2;\n\t"
+        "subc.u32 t1h, x2, 0;\n\t"
+        "add.cc.u32 %0, t0l, t1l;\n\t"
+        "addc.cc.u32 %1, t0h, t1h;\n\t"
+        "addc.u32 cm, 0, 0;\n\t"
+        "neg.s32 cm, cm;\n\t"
+        "add.cc.u32 %0, %0, cm;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}" : "=&r"(r0), "=&r"(r1) : "l"(a));
+    return ((u64)r1 << 32) | r0;
+#else
+    return gl_mul_nc(a, a);
+#endif
+}
+GL_HD u64 poseidon_sbox4(u64 x) {
+    u64 x2 = gl_sqr_nc4(x);
+    u64 x4 = gl_sqr_nc4(x2);
+    u64 x3 = gl_mul_nc4(x2, x);
+    return gl_mul_nc4(x4, x3);
+}
+
+GL_HD void pl_split(u64 x, i32 &l0, i32 &l1, i32 &l2) {
+    l0 = (i32)((u32)x & PL_M21); l1 = (i32)((u32)(x >> 21) & PL_M21); l2 = (i32)(u32)(x >> 42);
+}
+// limbs 0 <= y0, y1, y2 < 2^31 (y2 < 2^31 - 2^22)  ->  64-bit representative of y0 + y1*2^21 + y2*2^42 + HB  (mod p)
+GL_HD u64 pl_recombine(u32 y0, u32 y1, u32 y2) {
+    const u32 h = y2 >> 22;                       // weight 2^64 == 2^32 - 1
+    y2 &= PL_M22; y1 += h << 11; y0 += POSEIDON_L_HB - h;
+#ifdef __CUDA_ARCH__
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 s0, s1, s2, cm;\n\t"
+        "shl.b32 s0, %3, 21;\n\t"
+        "shr.b32 s1, %3, 11;\n\t"
+        "shl.b32 s2, %4, 10;\n\t"
+        "add.cc.u32 %0, %2, s0;\n\t"
+        "addc.u32 s1, s1, 0;\n\t"                 // y1 >> 11 < 2^20: no carry out
+        "add.cc.u32 %1, s1, s2;\n\t"              // (y2 << 10) + ... may wrap 2^32 once
+        "addc.u32 cm, 0, 0;\n\t"
+        "neg.s32 cm, cm;\n\t"
+        "add.cc.u32 %0, %0, cm;\n\t"              // += EPS on wrap (the wrapped high word is < 2^21: no second carry out)
+        "addc.u32 %1, %1, 0;\n\t"
+        "}" : "=&r"(r0), "=&r"(r1) : "r"(y0), "r"(y1), "r"(y2));
+    return ((u64)r1 << 32) | r0;
+#else
+    u64 v = (u64)y0 + ((u64)y1 << 21);
+    u64 t = (u64)y2 << 42;
+    u64 r = v + t;
+    if (r < t) r += GL_EPS;
+    return r;
+#endif
+}
+// carry-normalise an MDS output word in place: limbs back below (2^21 + HB, 2^21 + 2^20, 2^22); the value grows by HB
+GL_HD void pl_normalise(i32 &y0, i32 &y1, i32 &y2) {
+    const u32 t0 = (u32)y0, c0 = t0 >> 21;
+    const u32 t1 = (u32)y1 + c0, c1 = t1 >> 21;
+    const u32 t2 = (u32)y2 + c1, h = t2 >> 22;
+    y2 = (i32)(t2 & PL_M22);
+    y1 = (i32)((t1 & PL_M21) + (h << 11));
+    y0 = (i32)((t0 & PL_M21) + POSEIDON_L_HB - h);
+}
+// MDS layer on limb triples, in place (diagonal term included)
+GL_HD void pl_mds(i32 l0[12], i32 l1[12], i32 l2[12]) {
+    i32 y0[12], y1[12], y2[12];
+    poseidon_mds_limb(l0, y0); poseidon_mds_limb(l1, y1); poseidon_mds_limb(l2, y2);
+    y0[0] += l0[0] << 3; y1[0] += l1[0] << 3; y2[0] += l2[0] << 3;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { l0[i] = y0[i]; l1[i] = y1[i]; l2[i] = y2[i]; }
+}
+
+#ifdef __CUDA_ARCH__
+#define PLT(name) d_##name
+#else
+#define PLT(name) h_##name
+#endif
+// The permutation on a strided state (device: shared memory, element-major; host: stride 1), in/out canonical.
+GL_HD void poseidon_permute_limb(u64 *st, const int stride) {
+    i32 l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) pl_split(st[i * stride], l0[i], l1[i], l2[i]);
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            const pl_c4 *rc = PLT(POSEIDON_L_RC) + 12 * (4 * phase + r);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const pl_c4 c = rc[i];
+                st[i * stride] = pl_recombine((u32)l0[i] + c.a, (u32)l1[i] + c.b, (u32)l2[i] + c.c);
+            }
+#pragma unroll 2
+            for (int i = 0; i < 12; i++) st[i * stride] = poseidon_sbox4(st[i * stride]);
+#pragma unroll
+            for (int i = 0; i < 12; i++) pl_split(st[i * stride], l0[i], l1[i], l2[i]);
+            pl_mds(l0, l1, l2);
+        }
+        if (phase == 0) {
+#pragma unroll
+            for (int i = 1; i < 12; i++) pl_normalise(l0[i], l1[i], l2[i]);
+#pragma unroll 1
+            for (int r = 0; r < 22; r++) {
+                const pl_c4 c = PLT(POSEIDON_L_PK)[r];
+                const u64 x = poseidon_sbox4(pl_recombine((u32)l0[0] + c.a, (u32)l1[0] + c.b, (u32)l2[0] + c.c));
+                pl_split(x, l0[0], l1[0], l2[0]);
+                pl_mds(l0, l1, l2);
+#pragma unroll
+                for (int i = 1; i < 12; i++) pl_normalise(l0[i], l1[i], l2[i]);
+            }
+        }
+    }
+    const pl_c4 fin = POSEIDON_L_FIN_INIT;
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i * stride] = gl_canon(pl_recombine((u32)l0[i] + fin.a, (u32)l1[i] + fin.b, (u32)l2[i] + fin.c));
+}
+
+#ifdef __CUDACC__
+// Device entry used by the Merkle / sponge kernels: the 12-word state of a thread lives in SHARED memory (element-major:
+// word i of thread t at st[i * stride], conflict-free) so that the S-box layer of a full round is a rolled loop and the
+// whole permutation stays ~1.5 k instructions (the round-1 register-resident, fully unrolled version was 15 k instructions
+// and stalled on instruction fetch).  Out of line: one copy per kernel.
+static __device__ __noinline__ void poseidon_permute_smem(u64 *st, const int stride) { poseidon_permute_limb(st, stride); }
 #endif
 
 // host-side sponge helpers (used by the challenger / public-input hash)
