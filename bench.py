@@ -170,24 +170,24 @@ def run_b200(args):
             c = bp.Context(local); d = copy.copy(cd); d._handle = None; d.upload(c)
             pool.append((c, d))
             prove_on(len(pool), False)
-    def prove_on(slot, dev):
-        if slot == 0: return prove(dev)
+    def prove_on(slot, dev, full=False):
+        if slot == 0: return prove(dev, full)
         c, d = pool[slot - 1]
         o = ctypes.POINTER(ctypes.c_uint8)(); l2 = c_size_t()
         fn = lib.b200_prove_dev if dev else lib.b200_prove
         ptr = dev_wires.data_ptr() if dev else host_wires.data_ptr()
         rc = fn(c.h, d._handle, c_void_p(ptr), pis.ctypes.data_as(c_void_p), len(pis), ctypes.c_uint64(0), ctypes.byref(o), ctypes.byref(l2))
         if rc: raise RuntimeError(lib.b200_last_error(c.h).decode())
-        b = ctypes.string_at(o, 64); lib.b200_free(o)
+        b = ctypes.string_at(o, l2.value if full else 64); lib.b200_free(o)
         return b
-    def prove_many(indices, dev, S):
-        """prove one sig-shaped proof per entry of `indices` on S concurrent contexts; returns {index: proof head}"""
-        if S <= 1 or len(indices) <= 1: return {i: prove(dev) for i in indices}
+    def prove_many(indices, dev, S, full=False):
+        """prove one sig-shaped proof per entry of `indices` on S concurrent contexts; returns {index: proof bytes (head only unless full)}"""
+        if S <= 1 or len(indices) <= 1: return {i: prove(dev, full) for i in indices}
         pool_ensure(S)
         heads, errs = {}, []
         def work(slot):
             try:
-                for i in indices[slot::S]: heads[i] = prove_on(slot, dev)
+                for i in indices[slot::S]: heads[i] = prove_on(slot, dev, full)
             except Exception as e: errs.append(e)
         ths = [threading.Thread(target=work, args=(sl,)) for sl in range(S)]
         for t in ths: t.start()
@@ -198,13 +198,13 @@ def run_b200(args):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        recs = []
+        mine = {}
         for s in range(steps):
-            head = prove(dev)
-            recs.append(sharding.digest_record(s * world + rank, head))       # signature index s*world+rank -> this rank
+            mine[s * world + rank] = prove(dev, full=True)                     # signature index s*world+rank -> this rank
         if gather:
-            rows = sharding.gather_records(recs, dist, "cuda", steps)         # the single NVLink collective
-            assert len(rows) == steps * world
+            # the single NVLink collective: the COMPLETE sub-proofs (what recursive_proof consumes: signatures.rs:97-105,225-232)
+            allp = sharding.gather_proofs(mine, dist, "cuda", steps, proof_len[0])
+            assert sorted(allp) == list(range(steps * world)) and all(len(b) == proof_len[0] for b in allp.values())
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -213,7 +213,7 @@ def run_b200(args):
         return ms
 
     for _ in range(args.warmup): prove(True)
-    sharding.gather_records([sharding.digest_record(0, bytes(64))], dist, "cuda", 1)   # warm torch's own CUDA kernels / NCCL
+    sharding.gather_proofs({rank: prove(True, full=True)}, dist, "cuda", 1, proof_len[0])   # warm torch's own CUDA kernels / NCCL
     torch.cuda.synchronize()
     sampler = ClockSampler(local); sampler.start()
     ctx.enable_timing(True); ctx.timings()
@@ -236,49 +236,90 @@ def run_b200(args):
     if not ok_verify:
         raise SystemExit("bench: a proof of the headline circuit was rejected by b200_verify (or dev/host proofs differ) -- no number reported")
 
-    # ---- one whole BFT-finality block, measured (second half of BASELINE.json's metric; configs[1] at N=1, configs[2] at N=8):
-    # k signed approvals -> k sig-shaped sub-proofs sharded round-robin over the ranks (host witnesses through b200_prove),
-    # ONE all-gather of the digest records, then on rank 0 the sequential fold: (k + 55) recursive_proof-shaped proofs
-    # (2^13 rows, 135 wires) and the final PoseidonBN128 wrap (2^12 rows).  Wall clock between two barriers, max over ranks.
+    # ---- one whole BFT-finality block, measured (second half of BASELINE.json's metric; configs[1] at N=1, configs[2] at N=8).
+    # Task graph: b200_plonky2/block_dag.py (reference: prove_bft/bft.rs:38-565).  S: k sig-shaped sub-proofs sharded over the ranks
+    # (host witnesses through b200_prove) -> all-gather of the complete proofs -> C: the k-step recursive chain on rank 0, WHILE
+    # stage A (31 SHA-256-shaped, 9 tiny, 1 stake-shaped leaf proofs) runs on ranks 1..N-1 (N = 1: on a second context of the same
+    # GPU) -> all-gather of the leaf proofs -> F: 55 further recursive aggregations + the PoseidonBN128 wrap on rank 0.
+    # Wall clock between barriers, max over ranks.
     block = None
     if not args.no_block:
         try:
+            from b200_plonky2 import block_dag
             k = args.block_signatures
             rec_cd = wrap_cd = None
             ready = 1
-            if rank == 0:
-                try:
+            leaf_ctx = ctx if world > 1 else bp.Context(local)          # N = 1: stage A gets its own context / stream / host thread
+            my_leaf = block_dag.assign_leaf_tasks(world, rank)
+            leaf_cds = {}
+            try:
+                for _, kind, db in my_leaf:
+                    if (kind, db) not in leaf_cds:
+                        c_ = workloads.build(kind, db, seed=5); c_.upload(leaf_ctx); c_.prove(leaf_ctx); leaf_cds[(kind, db)] = c_
+                if rank == 0:
                     rec_cd = workloads.build("rec", 13, seed=3); rec_cd.upload(ctx)
                     wrap_cd = workloads.build("rec", 12, seed=3, hasher="bn254"); wrap_cd.upload(ctx)
                     rec_w = ctx.pinned_copy(rec_cd.wires); wrap_w = ctx.pinned_copy(wrap_cd.wires)
                     rec_cd.prove(ctx, wires=rec_w); wrap_cd.prove(ctx, wires=wrap_w)
-                except Exception as e:
-                    ready = 0; print(f"[bench] block set-up failed on rank 0: {e}", file=sys.stderr)
+            except Exception as e:
+                ready = 0; print(f"[bench] block set-up failed on rank {rank}: {e}", file=sys.stderr)
             if dist:      # every rank takes the same branch: a one-sided failure must not leave the others in a barrier
                 fl = torch.tensor([ready], dtype=torch.int64, device="cuda"); dist.all_reduce(fl, op=dist.ReduceOp.MIN); ready = int(fl.item())
             if not ready: raise RuntimeError("block set-up failed")
             mine = sharding.shard_indices(k, world, rank)
             if args.block_streams > 1: pool_ensure(args.block_streams)
+            leaf_stride = 200000
+            # warm the proof collective at its real shape (communicator buffers) outside the timed region
+            sharding.gather_proofs({}, dist, "cuda", (k + world - 1) // world, proof_len[0])
             barrier(); t0 = time.perf_counter()
-            heads = prove_many(mine, False, args.block_streams)
-            recs = [sharding.digest_record(i, heads[i]) for i in mine]
+            # S
+            sig = prove_many(mine, False, args.block_streams, full=True)
             t_sig = time.perf_counter() - t0
-            rows = sharding.gather_records(recs, dist, "cuda", (k + world - 1) // world)
-            assert len(rows) == k and [int(r[0]) for r in rows] == list(range(k))
-            t_gather = time.perf_counter() - t0
+            allsig = sharding.gather_proofs(sig, dist, "cuda", (k + world - 1) // world, proof_len[0])
+            assert sorted(allsig) == list(range(k))
+            t_g1 = time.perf_counter() - t0
+            # C (rank 0) || A (ranks 1..N-1, or a second context)
+            leaf_out, errs, t_leaf_busy = {}, [], [0.0]
+            def run_leaves():
+                try:
+                    ta = time.perf_counter()
+                    for tid_, kind, db in my_leaf: leaf_out[tid_] = leaf_cds[(kind, db)].prove(leaf_ctx)
+                    t_leaf_busy[0] = time.perf_counter() - ta
+                except Exception as e: errs.append(e)
+            th = threading.Thread(target=run_leaves); th.start()
+            t_chain = 0.0
             if rank == 0:
-                for _ in range(k + 55): rec_cd.prove(ctx, wires=rec_w)
+                tc = time.perf_counter()
+                for i in range(k): rec_cd.prove(ctx, wires=rec_w)            # chain step i consumes sub-proof i (validator order)
+                t_chain = time.perf_counter() - tc
+            th.join()
+            if errs: raise errs[0]
+            t_ca = time.perf_counter() - t0
+            allleaf = sharding.gather_proofs(leaf_out, dist, "cuda", block_dag.max_leaf_tasks_per_rank(world), leaf_stride)
+            assert sorted(allleaf) == list(range(len(block_dag.LEAF_SHAPES)))
+            t_g2 = time.perf_counter() - t0
+            # F
+            if rank == 0:
+                for _ in range(block_dag.FINAL_AGGREGATIONS): rec_cd.prove(ctx, wires=rec_w)
                 wrap_cd.prove(ctx, wires=wrap_w)
             barrier(); t_all = time.perf_counter() - t0
-            tt = torch.tensor([t_sig, t_gather, t_all], dtype=torch.float64, device="cuda")
+            tt = torch.tensor([t_sig, t_g1, t_ca, t_g2, t_all, t_chain, t_leaf_busy[0]], dtype=torch.float64, device="cuda")
             if dist: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_sig, t_gather, t_all = (float(x) for x in tt.tolist())
+            t_sig, t_g1, t_ca, t_g2, t_all, t_chain, t_leaf = (float(x) for x in tt.tolist())
             block = {"bft_block_ms": round(t_all * 1e3, 1), "signature_stage_ms": round(t_sig * 1e3, 1),
-                     "digest_all_gather_ms": round((t_gather - t_sig) * 1e3, 2) if world > 1 else 0.0,
-                     "fold_and_wrap_ms": round((t_all - t_gather) * 1e3, 1), "signatures": k, "sig_proofs_per_rank_max": len(sharding.shard_indices(k, world, 0)),
-                     "recursive_proofs": k + 55, "streams_per_gpu_in_signature_stage": args.block_streams, "note": "measured: k sig-shaped proofs sharded over the ranks (host witnesses), one all-gather, then the "
-                     "sequential fold of k+55 recursive_proof-shaped proofs + 1 BN128 wrap on rank 0; prover time only (witness generation and circuit builds stay in Rust)"}
+                     "subproof_all_gather_ms": round((t_g1 - t_sig) * 1e3, 2),
+                     "subproof_all_gather_bytes": sharding.payload_bytes((k + world - 1) // world, proof_len[0], world),
+                     "chain_and_leaf_stage_ms": round((t_ca - t_g1) * 1e3, 1), "chain_ms_rank0": round(t_chain * 1e3, 1),
+                     "leaf_stage_busy_ms_max_rank": round(t_leaf * 1e3, 1), "leaf_all_gather_ms": round((t_g2 - t_ca) * 1e3, 2),
+                     "final_aggregation_and_wrap_ms": round((t_all - t_g2) * 1e3, 1),
+                     "signatures": k, "sig_proofs_per_rank_max": len(sharding.shard_indices(k, world, 0)),
+                     "streams_per_gpu_in_signature_stage": args.block_streams, "task_graph": block_dag.summary(k),
+                     "leaf_stage_placement": "ranks 1..N-1 while rank 0 walks the chain" if world > 1 else "second context on the same GPU, concurrent with the chain",
+                     "note": "measured end to end between barriers (max over ranks): prover time of every proof of the block's task graph with host witnesses; "
+                             "witness generation and circuit builds stay in Rust and are not included; the recursive steps re-prove one recursion-shaped witness"}
             if rank == 0: rec_cd.free(); wrap_cd.free()
+            for c_ in leaf_cds.values(): c_.free()
+            if leaf_ctx is not ctx: leaf_ctx.close()
         except Exception as e:
             block = {"bft_block_ms": None, "error": str(e)}
 

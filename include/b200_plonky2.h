@@ -99,10 +99,27 @@ const char *b200_ctx_timings(b200_ctx *ctx);
  * constants_sigmas_values: [num_constants + num_routed_wires][n] column-major VALUES on the subgroup H (natural
  * order), i.e. plonky2's constant polys followed by the sigma polys.  Computes the constants/sigmas LDE + Merkle
  * cap on the GPU and keeps everything resident.  cap_out (optional): 2^cap_height * 4 u64.
- * circuit_digest: 4 u64 (GL hasher), as computed by build(). */
+ * circuit_digest: 4 u64 as computed by build(), or NULL to have the library derive it from the cap. */
 int b200_circuit_upload(b200_ctx *ctx, const b200_common *common, const uint64_t *constants_sigmas_values,
-                        const uint64_t circuit_digest[4], uint64_t *cap_out, b200_circuit **out);
+                        const uint64_t *circuit_digest /* 4 u64, or NULL: derive it from the cap */, uint64_t *cap_out, b200_circuit **out);
 void b200_circuit_free(b200_circuit *c);
+/* CircuitBuilder::build::<C>()'s device half, from the builder's own data instead of finished polynomials
+ * (near_bft_finality/src/prove_crypto/recursion.rs:94, ed25519.rs:33,75, sha256.rs:78: the constant / sigma polynomial
+ * generation + commitment + digest that follow gate placement and copy-constraint resolution):
+ *   row_gate        [n]                      index into common->gate_ids of the gate instantiated on each row
+ *   gate_constants  [num_constants - num_selector_groups][n]  the gates' own constants, column-major (NULL if none)
+ *   sigma_next      [num_routed_wires][n]    for routed slot s = col * n + row: the slot of the NEXT wire of its copy class
+ *                                            (WirePartition::get_sigma_polys' cyclic successor; s itself if unconstrained)
+ * The selector columns, the sigma polynomial values k_is[col'] * w^row', their LDE + Merkle cap and the circuit digest are
+ * produced on the GPU / by the library.  Circuits are CACHED per context, keyed by a 128-bit hash of all inputs: the reference
+ * rebuilds an identical recursion circuit on each of its k + 55 recursive_proof calls (recursion.rs:36-96); a repeated build
+ * returns the resident circuit (*cache_hit = 1) after hashing its inputs.  Handles are reference counted: release each with
+ * b200_circuit_free.  cap_out: 2^cap_height * 4 u64; digest_out: 4 u64 (both optional). */
+int b200_circuit_build(b200_ctx *ctx, const b200_common *common, const uint32_t *row_gate, const uint64_t *gate_constants,
+                       const uint32_t *sigma_next, uint64_t *cap_out, uint64_t *digest_out, int *cache_hit, b200_circuit **out);
+/* circuit_digest = H(constants_sigmas_cap || H_pad([]) || degree_bits) with the config's hasher (host only). */
+int b200_circuit_digest(uint32_t hasher, const uint64_t *cap, uint32_t cap_height, uint32_t degree_bits, uint64_t out[4]);
+int b200_ctx_cache_stats(const b200_ctx *ctx, uint64_t *hits, uint64_t *misses, uint64_t *entries);
 
 /* ---- prove ----
  * wires: [num_wires][n] column-major (the full witness), public_inputs: [num_public_inputs].

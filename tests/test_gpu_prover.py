@@ -147,3 +147,31 @@ def test_pinned_witness_buffer_gives_same_proof():
     b = cd.prove(ctx, wires=w)
     assert a == b
     cd.free()
+
+
+@pytest.mark.parametrize("kind,db,hasher", [("rec", 8, "gl"), ("sig", 9, "gl"), ("tiny_pi", 4, "gl"), ("rec", 7, "bn254")])
+def test_circuit_build_on_device_equals_upload_and_is_cached(kind, db, hasher):
+    """b200_circuit_build (selector / sigma polynomials generated on the GPU from gate placement + copy-class successor map,
+    digest derived by the library) == b200_circuit_upload of the host-built polynomials: same cap, same digest (== oracle),
+    same proof bytes; a second build of the same circuit is a cache hit and returns the same handle."""
+    import b200_plonky2 as bp
+    from b200_plonky2 import workloads
+    from oracle import prover
+    ctx = bp.Context(0)
+    a = workloads.build(kind, db, seed=5, hasher=hasher); a.upload(ctx)
+    oc = prover.OracleCircuit(a.common, a.constants_sigmas)
+    assert np.array_equal(a.constants_sigmas_cap, oc.cap) and list(a.circuit_digest) == list(oc.digest)
+    b = workloads.build(kind, db, seed=5, hasher=hasher)
+    assert b.build_on_device(ctx) is False
+    assert np.array_equal(b.constants_sigmas_cap, a.constants_sigmas_cap) and b.circuit_digest == a.circuit_digest
+    pa = a.prove(ctx); pb = b.prove(ctx)
+    assert pa == pb == oc.prove(a.wires, a.public_inputs)
+    c = workloads.build(kind, db, seed=5, hasher=hasher)
+    assert c.build_on_device(ctx) is True and c._handle.value == b._handle.value
+    assert c.prove(ctx) == pa
+    st = ctx.cache_stats(); assert st["hits"] == 1 and st["misses"] == 1 and st["entries"] == 1
+    d = workloads.build(kind, db, seed=6, hasher=hasher)           # other constants / witness: a different circuit or the same one
+    hit = d.build_on_device(ctx)
+    assert hit == np.array_equal(d.constants_sigmas, a.constants_sigmas)
+    for x in (a, b, c, d): x.free()
+    ctx.close()

@@ -22,6 +22,17 @@ def test_limb_resident_permutation_matches_poseidon_permute(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "limb-resident permutation == poseidon_permute" in r.stdout, r.stdout + r.stderr
 
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not on PATH")
+def test_device_gate_evaluators_match_generic_on_host(tmp_path):
+    """eval_gate<KIND> of gates.cuh (the quotient kernels' evaluators: lazy 128-bit recompositions, non-canonical products,
+    batched column loads) compiled for the host == the generic evaluators b200_verify uses, for all 20 constraint-bearing gate
+    kinds (several parameterisations) on random, small-valued and near-p rows."""
+    exe = str(tmp_path / "gate_emu")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "zk-light-client-implementation_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "gate_eval_emulation.cu"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "device gate evaluators == generic evaluators" in r.stdout, r.stdout + r.stderr
+
 def test_limb_table_generator_is_reproducible(tmp_path):
     """the committed poseidon_limb_tables.cuh is what the generator derives from the published round constants (its own
     value-level replay of the limb algorithm against the textbook rounds runs inside the generator)"""

@@ -52,3 +52,25 @@ def test_accepts_oracle_prover_proofs_and_rejects_wrong_witness(kind, db, hasher
     w = cd.wires.copy(); w[0, min(5, cd.n - 1)] ^= 1
     ok, why = bp.verify(cd.common, oc.cap, oc.digest, oc.prove(w, cd.public_inputs))
     assert not ok
+
+
+@pytest.mark.parametrize("name", NEAR + ["gnark"])
+def test_circuit_digest_reproduces_golden_verifier_data(name):
+    """b200_circuit_digest (the digest formula b200_circuit_build / b200_circuit_upload apply, BN128 hasher) on the golden
+    constants_sigmas_cap == the circuit_digest stored next to it by the reference (G6: the three final wrapper circuits, all
+    the same deterministic circuit; G5: the gnark fixture)."""
+    if name == "gnark":
+        d = os.path.join(G, "gnark_test_circuit")
+        vd = json.load(open(f"{d}/verifier_only_circuit_data.json")); cj = json.load(open(f"{d}/common_circuit_data.json"))
+    else:
+        d = os.path.join(G, "near_final_proofs", name)
+        vd = json.load(open(f"{d}/verifier_data.json")); cj = json.load(open(f"{d}/common_data.json"))
+    cap = [_limbs(h) for h in vd["constants_sigmas_cap"]]
+    got = bp.circuit_digest("bn254", cap, cj["fri_params"]["degree_bits"])
+    assert got == _limbs(vd["circuit_digest"])
+
+def test_circuit_digest_gl_matches_host_mirror():
+    from b200_plonky2 import digest
+    rng = np.random.default_rng(3)
+    cap = rng.integers(0, 1 << 63, size=(16, 4), dtype=np.uint64)
+    assert bp.circuit_digest("gl", cap, 13) == [int(x) for x in digest.circuit_digest(cap, 13)]

@@ -33,6 +33,28 @@ def test_shard_and_gather_world2(tmp_path, k):
     for i in range(k):
         assert list(r0[i]) == sharding.digest_record(i, bytes([(i * 7 + j) % 256 for j in range(64)]))
 
+def _worker_proofs(rank, world, port, k, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200_plonky2 import sharding
+    mine = sharding.shard_indices(k, world, rank)
+    proofs = {i: bytes([(i * 13 + j) % 251 for j in range(1000 + 37 * i)]) for i in mine}      # ragged lengths
+    got = sharding.gather_proofs(proofs, dist, "cpu", -(-k // world), 1000 + 37 * k)
+    import pickle
+    pickle.dump(got, open(os.path.join(out_dir, f"proofs{rank}.pkl"), "wb"))
+    dist.destroy_process_group()
+
+@pytest.mark.parametrize("k", [7, 1])
+def test_gather_full_proofs_world2(tmp_path, k):
+    """the real payload: complete (ragged-length) proof bytes of every sub-proof reach every rank in one all-gather"""
+    import pickle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.environ["PYTHONPATH"] = os.pathsep.join([root, os.path.join(root, "zk-light-client-implementation_b200"), os.environ.get("PYTHONPATH", "")])
+    mp.spawn(_worker_proofs, args=(2, _free_port(), k, str(tmp_path)), nprocs=2, join=True)
+    g0 = pickle.load(open(tmp_path / "proofs0.pkl", "rb")); g1 = pickle.load(open(tmp_path / "proofs1.pkl", "rb"))
+    assert g0 == g1 and sorted(g0) == list(range(k))
+    for i in range(k): assert g0[i] == bytes([(i * 13 + j) % 251 for j in range(1000 + 37 * i)])
+
 def test_shard_indices_partition():
     from b200_plonky2 import sharding
     for k in (0, 1, 62, 81, 100):

@@ -211,7 +211,13 @@ class CircuitBuilder:
             num_partial_products=npp, num_gate_constraints=max(_gate_num_constraints(g.id) for g in gates),
             num_public_inputs=len(self.public_inputs), reduction_arity_bits=rab, gates=[g.id for g in gates],
             selector_indices=sel_index, groups=groups, k_is=[int(x) for x in k_is])
-        return CircuitData(common, cs, wires, list(self.public_inputs))
+        cd = CircuitData(common, cs, wires, list(self.public_inputs))
+        # what CircuitBuilder::build hands to b200_circuit_build: gate placement, the gates' constants, the copy-class successor map
+        row_gate = np.zeros(n, np.uint32); r = 0
+        for kind, c, w_ in self.blocks:
+            row_gate[r:r + w_.shape[0]] = index[kind.id]; r += w_.shape[0]
+        cd.build_inputs = dict(row_gate=row_gate, gate_constants=np.ascontiguousarray(consts[nsel:]), sigma_next=nxt.astype(np.uint32).reshape(R, n))
+        return cd
 
 def _gate_num_constraints(gid):
     # counted by the gate definitions (crypto/plonky2_u32/src/gates/*.rs num_constraints(); plonky2 standard gates)
@@ -244,6 +250,7 @@ def _gate_num_constraints(gid):
 # ---------------------------------------------------------------------------------------------------------------
 class CircuitData:
     """What build() returns: prover-side data.  prove() mirrors plonky2 CircuitData::prove(pw) -> proof bytes."""
+    build_inputs = None
     def __init__(self, common, constants_sigmas, wires, public_inputs):
         self.common = common
         self.constants_sigmas = constants_sigmas      # [num_constants + routed][n] values on H
@@ -283,29 +290,37 @@ class CircuitData:
         return cc
 
     def upload(self, ctx):
-        """CircuitBuilder::build()'s GPU part: constants/sigmas commitment; derives the circuit digest."""
+        """CircuitBuilder::build()'s commitment half from finished constant / sigma polynomial VALUES (b200_circuit_upload);
+        the library derives the circuit digest from the cap."""
         from . import lib, c_void_p
-        from .digest import circuit_digest
         if self._handle is not None: return self
         cc = self.c_common()
         cap = np.zeros((1 << self.common["cap_height"], 4), np.uint64)
         h = c_void_p()
-        # two-step: the digest depends on the cap, so upload first with a zero digest, then set it
-        dg0 = (ctypes.c_uint64 * 4)(0, 0, 0, 0)
-        ctx._chk(lib.b200_circuit_upload(ctx.h, ctypes.byref(cc), self.constants_sigmas.ctypes.data_as(c_void_p), dg0,
+        ctx._chk(lib.b200_circuit_upload(ctx.h, ctypes.byref(cc), self.constants_sigmas.ctypes.data_as(c_void_p), None,
                                          cap.ctypes.data_as(c_void_p), ctypes.byref(h)))
         self.constants_sigmas_cap = cap
-        if self.common.get("hasher", "gl") == "bn254":
-            from .poseidon_bn254_py import circuit_digest as digest_bn254
-            self.circuit_digest = digest_bn254(cap, self.common["degree_bits"])
-        else:
-            self.circuit_digest = circuit_digest(cap, self.common["degree_bits"])
-        lib.b200_circuit_free(h)
-        dg = (ctypes.c_uint64 * 4)(*self.circuit_digest)
-        ctx._chk(lib.b200_circuit_upload(ctx.h, ctypes.byref(cc), self.constants_sigmas.ctypes.data_as(c_void_p), dg,
-                                         cap.ctypes.data_as(c_void_p), ctypes.byref(h)))
+        from . import circuit_digest
+        self.circuit_digest = circuit_digest(self.common.get("hasher", "gl"), cap, self.common["degree_bits"])
         self._handle = h; self._ctx = ctx
         return self
+
+    def build_on_device(self, ctx):
+        """CircuitBuilder::build()'s device half from the builder's own data (b200_circuit_build): selector / sigma polynomial
+        generation, commitment and digest on the GPU, with the per-context circuit cache.  Returns True on a cache hit."""
+        from . import lib, c_void_p
+        assert self._handle is None and self.build_inputs is not None
+        bi = self.build_inputs
+        cc = self.c_common()
+        cap = np.zeros((1 << self.common["cap_height"], 4), np.uint64); dg = np.zeros(4, np.uint64)
+        h = c_void_p(); hit = ctypes.c_int(0)
+        gc = bi["gate_constants"]
+        ctx._chk(lib.b200_circuit_build(ctx.h, ctypes.byref(cc), bi["row_gate"].ctypes.data_as(c_void_p),
+                                        gc.ctypes.data_as(c_void_p) if gc.size else None, bi["sigma_next"].ctypes.data_as(c_void_p),
+                                        cap.ctypes.data_as(c_void_p), dg.ctypes.data_as(c_void_p), ctypes.byref(hit), ctypes.byref(h)))
+        self.constants_sigmas_cap = cap; self.circuit_digest = [int(x) for x in dg]
+        self._handle = h; self._ctx = ctx
+        return bool(hit.value)
 
     def prove(self, ctx, wires=None, public_inputs=None, pow_witness_hint=0):
         """CircuitData::prove(pw): returns ProofWithPublicInputs::to_bytes()."""

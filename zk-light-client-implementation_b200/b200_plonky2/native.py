@@ -66,11 +66,14 @@ _sig("b200_msm_g2", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
 _sig("b200_msm_g2_dev", c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
 _sig("b200_fr_ntt", c_int, c_void_p, c_void_p, c_u32, c_int, c_int, c_void_p)
 _sig("b200_fr_ntt_dev", c_int, c_void_p, c_void_p, c_u32, c_int, c_int, c_void_p)
+_sig("b200_circuit_build", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("b200_circuit_digest", c_int, c_u32, c_void_p, c_u32, c_u32, c_void_p)
+_sig("b200_ctx_cache_stats", c_int, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
 _sig("b200_verify_error", ctypes.c_char_p)
 
 EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_synchronize", "b200_last_error",
-           "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_free", "b200_prove",
+           "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_build", "b200_circuit_digest", "b200_ctx_cache_stats", "b200_circuit_free", "b200_prove",
            "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
            "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
            "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev", "b200_msm_g2", "b200_msm_g2_dev", "b200_fr_ntt", "b200_fr_ntt_dev"]
@@ -116,6 +119,10 @@ class Context:
         return out
     def enable_timing(self, on=True):
         self._chk(lib.b200_ctx_enable_timing(self.h, int(on)))
+    def cache_stats(self):
+        h, m, e = c_u64(), c_u64(), c_u64()
+        lib.b200_ctx_cache_stats(self.h, ctypes.byref(h), ctypes.byref(m), ctypes.byref(e))
+        return {"hits": h.value, "misses": m.value, "entries": e.value}
     def timings(self):
         import json
         return json.loads(lib.b200_ctx_timings(self.h).decode())
@@ -207,6 +214,16 @@ def common_from_json(d: dict, hasher="gl"):
                 num_public_inputs=d["num_public_inputs"], reduction_arity_bits=list(fp["reduction_arity_bits"]),
                 gates=list(d["gates"]), selector_indices=list(d["selectors_info"]["selector_indices"]),
                 groups=[(g["start"], g["end"]) for g in d["selectors_info"]["groups"]], k_is=list(d["k_is"]), hasher=hasher)
+
+def circuit_digest(hasher, cap, degree_bits):
+    """CircuitBuilder::build's circuit_digest from the constants/sigmas cap ([2^cap_height][4] u64), host only."""
+    cap = np.ascontiguousarray(cap, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros(4, dtype=np.uint64)
+    ch = int(cap.shape[0]).bit_length() - 1
+    assert cap.shape[0] == 1 << ch
+    rc = lib.b200_circuit_digest(1 if hasher == "bn254" else 0, cap.ctypes.data_as(c_void_p), ch, degree_bits, out.ctypes.data_as(c_void_p))
+    if rc: raise B200Error(rc, "b200_circuit_digest: bad arguments")
+    return [int(x) for x in out]
 
 def verify(common: dict, constants_sigmas_cap, circuit_digest, proof_bytes: bytes):
     """CircuitData::verify: constants_sigmas_cap [2^cap_height][4] u64 words, circuit_digest 4 words.  Returns (ok, reason)."""

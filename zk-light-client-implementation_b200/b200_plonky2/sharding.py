@@ -1,7 +1,12 @@
 """Multi-GPU sharding of the independent signature sub-proofs: signature index -> rank round-robin, one
-all-gather of fixed-size digest records before the sequential recursive fold.  Replaces the reference's NATS fan-out
-(near_bft_finality/src/prove_block_data/signatures.rs:144-274: PROVE_SIGNATURE / PROCESS_SIGNATURE_RESULT).
-Backend-agnostic (nccl on GPUs, gloo in the CPU tests)."""
+all-gather of the sub-proofs before the sequential recursive fold.  Replaces the reference's NATS fan-out
+(near_bft_finality/src/prove_block_data/signatures.rs:144-274: PROVE_SIGNATURE / PROCESS_SIGNATURE_RESULT, whose result
+message carries the whole serialized proof + verifier data: signatures.rs:225-232).
+Backend-agnostic (nccl on GPUs, gloo in the CPU tests).
+
+Two payloads: gather_proofs moves the COMPLETE proof bytes of every sub-proof to every rank in one collective (what
+recursive_proof needs as witness: signatures.rs:97-105); gather_records moves only (index, first cap digest) records (the
+digest-only variant north_star describes)."""
 import numpy as np
 
 RECORD_WORDS = 5        # [signature_index, 4 x u63 digest words]
@@ -30,3 +35,41 @@ def gather_records(records, dist, device, max_per_rank):
     rows = torch.cat(allr).cpu().numpy()
     rows = rows[rows[:, 0] >= 0]
     return rows[np.argsort(rows[:, 0], kind="stable")]
+
+
+# ---- full sub-proof payload ----
+def pack_proofs(proofs, max_count, stride, device, pin=False):
+    """proofs: {index: bytes} of this rank -> uint8 tensor [max_count, 16 + stride]: per row
+    int64 index (-1 = empty), int64 length, proof bytes (zero padded)."""
+    import torch
+    stride = (stride + 7) & ~7                                   # rows stay 8-byte aligned (the header is viewed as int64)
+    t = torch.zeros((max_count, 16 + stride), dtype=torch.uint8, pin_memory=pin)
+    hdr = t[:, :16].view(torch.int64)
+    hdr[:, 0] = -1
+    for row, (idx, b) in enumerate(sorted(proofs.items())):
+        if len(b) > stride: raise ValueError(f"proof {idx}: {len(b)} bytes > stride {stride}")
+        hdr[row, 0] = idx; hdr[row, 1] = len(b)
+        t[row, 16:16 + len(b)] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
+    return t.to(device, non_blocking=True) if str(device) != "cpu" else t
+
+def gather_proofs(proofs, dist, device, max_count, stride):
+    """ONE all-gather of every rank's packed proofs; returns {index: bytes} of all ranks (identical on every rank)."""
+    import torch
+    t = pack_proofs(proofs, max_count, stride, device)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        allt = t.unsqueeze(0)
+    else:
+        allt = torch.empty((dist.get_world_size() * t.shape[0], t.shape[1]), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allt, t)                     # rank r's rows land at [r * max_count, (r + 1) * max_count)
+        allt = allt.view(dist.get_world_size(), t.shape[0], t.shape[1])
+    h = allt.cpu()
+    out = {}
+    for r in range(h.shape[0]):
+        hdr = h[r][:, :16].contiguous().view(torch.int64)
+        for row in range(h.shape[1]):
+            idx, ln = int(hdr[row, 0]), int(hdr[row, 1])
+            if idx >= 0: out[idx] = bytes(h[r][row, 16:16 + ln].numpy().tobytes())
+    return out
+
+def payload_bytes(max_count, stride, world):
+    return world * max_count * (16 + ((stride + 7) & ~7))

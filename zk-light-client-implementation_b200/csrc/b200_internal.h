@@ -51,6 +51,10 @@ void ntt_tables_free(NttTables &T);
 //   result stored in bit-reversed order (standard in-place DIF), multiplied by out_mul (1 = none)
 void ntt_dif(const NttTables &T, const u64 *in, size_t in_stride, bool in_bitrev, u64 *out, size_t out_stride,
              int L, size_t items, int rate_bits, const u64 *scale, bool inverse, u64 out_mul, cudaStream_t st);
+// bulk-copy (TMA) staged passes for 16 <= L <= 20 (ntt2.cu); ntt_dif dispatches to them
+bool ntt2_supported(int L, size_t in_stride, size_t out_stride, int rate_bits);
+void ntt2_dif(const NttTables &T, const u64 *in, size_t in_stride, bool in_bitrev, u64 *out, size_t out_stride,
+              int L, size_t items, int rate_bits, const u64 *scale, bool inverse, u64 out_mul, cudaStream_t st);
 void bitrev_permute(const u64 *in, u64 *out, int L, size_t items, cudaStream_t st);   // out[it][bitrev(i)] = in[it][i]
 // powers table: out[r * n + p] = (shift * w_{n<<rate_bits}^r)^{bitrev_L(p)} * mul   (coset scaling for the LDE)
 void lde_scale_table(u64 *out, int L, int rate_bits, u64 shift, cudaStream_t st);

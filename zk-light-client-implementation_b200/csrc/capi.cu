@@ -40,6 +40,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx_drop_circuit_cache(ctx);
     ntt_tables_free(ctx->tw);
     for (auto &kv : ctx->lde_scale) cudaFree(kv.second);
     if (ctx->arena) cudaFree(ctx->arena);

@@ -10,6 +10,7 @@
 #include <chrono>
 
 struct ApiErr { int code; std::string msg; };
+struct b200_circuit;
 
 struct b200_ctx {
     int device = 0;
@@ -22,6 +23,7 @@ struct b200_ctx {
     u64 *tmp_q_big = nullptr;
     void *pinned = nullptr;                           // pinned staging for the small per-proof transfers
     cudaStream_t copy_stream = nullptr;               // H2D of host witnesses, overlapped with the LDE
+    std::vector<b200_circuit *> circuit_cache; unsigned long long cache_tick = 0, cache_hits = 0, cache_misses = 0;   // b200_circuit_build
     void *fr_tw[2] = {nullptr, nullptr}; int fr_tw_log[2] = {0, 0};   // BN254 F_r twiddles (fr_ntt.cu): forward, inverse
     // optional phase timing (b200_ctx_enable_timing): CUDA events on the context stream around prover phases
     bool timing = false;
@@ -56,3 +58,4 @@ void commit_coeffs(b200_ctx *ctx, const u64 *d_coeffs_br, size_t cols, int log_n
 void commit_values_lde_only(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, int rate_bits, u64 *d_coeffs_br, u64 *d_lde);
 void commit_hash_only(b200_ctx *ctx, const u64 *d_lde, size_t cols, int log_n, int rate_bits, int cap_height, u64 *d_digests, int hasher);
 void poseidon_permute_batch(u64 *d_states, size_t count, cudaStream_t st);
+void ctx_drop_circuit_cache(b200_ctx *ctx);          // prover.cu

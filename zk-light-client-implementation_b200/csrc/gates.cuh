@@ -32,10 +32,31 @@ struct GateDesc {
 
 #define MAX_CHALLENGES 2
 
+// Everything below compiles for the device (the quotient kernels of plonk.cu) AND for the host: tests/gate_eval_emulation.cu
+// runs these evaluators on the CPU against the generic evaluators of verify_gates.h (which b200_verify uses and the
+// reference's golden proofs pin), so the arithmetic shortcuts below are checked without a GPU.
+#if defined(__CUDACC__) || defined(B200_GATES_HOST)
+#ifdef __CUDA_ARCH__
+#define GATE_LD(p) __ldg(p)
+#else
+#define GATE_LD(p) (*(p))
+#endif
 #ifdef __CUDACC__
+#define GATE_NOINLINE static __host__ __device__ __noinline__
+#else
+#define GATE_NOINLINE static
+#endif
+
 struct Wires {              // column-major matrix accessor at one LDE position
     const u64 *base; size_t stride, pos;
-    __device__ __forceinline__ u64 operator[](u32 j) const { return __ldg(base + (size_t)j * stride + pos); }
+    GL_HD u64 operator[](u32 j) const { return GATE_LD(base + (size_t)j * stride + pos); }
+    // B consecutive columns at once: the loads are independent, so B of them are in flight per thread (the round-1 kernels
+    // walked the columns one dependent load at a time: 33-53 % long_scoreboard stalls, profiles/ncu_gates_r01_v9.jsonl)
+    template <int B> GL_HD void load(u32 j0, u64 (&out)[B]) const {
+        const u64 *p = base + (size_t)j0 * stride + pos;
+#pragma unroll
+        for (int k = 0; k < B; k++) out[k] = GATE_LD(p + (size_t)k * stride);
+    }
 };
 
 struct ConstraintSink {     // S_k += c * alpha_k^idx
@@ -43,41 +64,62 @@ struct ConstraintSink {     // S_k += c * alpha_k^idx
     u32 apow_stride;
     acc192 acc[MAX_CHALLENGES];
     u32 idx;
-    __device__ __forceinline__ void reset() {
+    GL_HD void reset() {
 #pragma unroll
         for (int k = 0; k < MAX_CHALLENGES; k++) { acc[k].lo = 0; acc[k].hi = 0; acc[k].top = 0; }
         idx = 0;
     }
-    __device__ __forceinline__ void push(u64 c) {
+    // c: ANY 64-bit representative of the constraint value (the product is exact, the accumulator is reduced at the end)
+    GL_HD void push(u64 c) {
 #pragma unroll
-        for (int k = 0; k < MAX_CHALLENGES; k++) acc192_mad(acc[k], c, __ldg(apow + k * apow_stride + idx));
+        for (int k = 0; k < MAX_CHALLENGES; k++) acc192_mad(acc[k], c, GATE_LD(apow + k * apow_stride + idx));
         idx++;
     }
-    __device__ __forceinline__ u64 result(int k) const { return acc192_reduce(acc[k]); }
+    // same, at an explicit constraint index (lets a gate produce its constraints in one pass over the wires in any order)
+    GL_HD void push_at(u64 c, u32 at) {
+#pragma unroll
+        for (int k = 0; k < MAX_CHALLENGES; k++) acc192_mad(acc[k], c, GATE_LD(apow + k * apow_stride + at));
+    }
+    GL_HD u64 result(int k) const { return acc192_reduce(acc[k]); }
 };
 
 struct alg2 { u64 a, b; };   // extension-algebra element over the base field: a + b X, X^2 = 7
-__device__ __forceinline__ alg2 A2(u64 a, u64 b) { alg2 r; r.a = a; r.b = b; return r; }
-__device__ __forceinline__ alg2 alg_add(alg2 x, alg2 y) { return A2(gl_add(x.a, y.a), gl_add(x.b, y.b)); }
-__device__ __forceinline__ alg2 alg_sub(alg2 x, alg2 y) { return A2(gl_sub(x.a, y.a), gl_sub(x.b, y.b)); }
-__device__ __forceinline__ alg2 alg_mul(alg2 x, alg2 y) {
+GL_HD alg2 A2(u64 a, u64 b) { alg2 r; r.a = a; r.b = b; return r; }
+GL_HD alg2 alg_add(alg2 x, alg2 y) { return A2(gl_add(x.a, y.a), gl_add(x.b, y.b)); }
+GL_HD alg2 alg_sub(alg2 x, alg2 y) { return A2(gl_sub(x.a, y.a), gl_sub(x.b, y.b)); }
+GL_HD alg2 alg_mul(alg2 x, alg2 y) {
     return A2(gl_add(gl_mul(x.a, y.a), gl_mul(7, gl_mul(x.b, y.b))), gl_add(gl_mul(x.a, y.b), gl_mul(x.b, y.a)));
 }
-__device__ __forceinline__ alg2 alg_scalar(u64 s, alg2 x) { return A2(gl_mul(s, x.a), gl_mul(s, x.b)); }
-__device__ __forceinline__ alg2 W2(const Wires &w, u32 i) { return A2(w[i], w[i + 1]); }
+GL_HD alg2 alg_scalar(u64 s, alg2 x) { return A2(gl_mul(s, x.a), gl_mul(s, x.b)); }
+GL_HD alg2 W2(const Wires &w, u32 i) { return A2(w[i], w[i + 1]); }
 
-// x(x-1)(x-2)(x-3) = t(t+2) with t = x(x-3): two multiplications
-__device__ __forceinline__ u64 range_prod4(u64 x) {
-    u64 t = gl_mul(x, gl_sub(x, 3));
-    return gl_mul(t, gl_add(t, 2));
+// ---- lazy helpers: results are arbitrary 64-bit representatives (fine for ConstraintSink::push and as multiplicands) ----
+// x + k for a small constant k, x any 64-bit representative
+GL_HD u64 gl_add_small_nc(u64 x, u32 k) { u64 s = x + k; if (s < k) s += GL_EPS; return s; }
+// x(x-1)(x-2)(x-3) = t(t+2) with t = x(x-3): two multiplications; x canonical
+GL_HD u64 range_prod4(u64 x) {
+    u64 t = gl_mul_nc(x, gl_sub(x, 3));
+    return gl_mul_nc(t, gl_add_small_nc(t, 2));
 }
-__device__ __forceinline__ u64 gl_dbl(u64 x) { return gl_add(x, x); }
-__device__ __forceinline__ u64 gl_x4(u64 x) { return gl_dbl(gl_dbl(x)); }
-__device__ __forceinline__ u64 range_prod2(u64 x) { return gl_mul(x, gl_sub(x, 1)); }
-__device__ __forceinline__ u64 range_prod_n(u64 x, int n) { u64 p = 1; for (int k = 0; k < n; k++) p = gl_mul(p, gl_sub(x, (u64)k)); return p; }
-__device__ __forceinline__ u64 sbox7c(u64 x) { return gl_canon(poseidon_sbox(x)); }
+GL_HD u64 range_prod2(u64 x) { return gl_mul_nc(x, gl_sub(x, 1)); }
+GL_HD u64 range_prod_n(u64 x, int n) { u64 p = 1; for (int k = 0; k < n; k++) p = gl_mul(p, gl_sub(x, (u64)k)); return p; }
+GL_HD u64 sbox7c(u64 x) { return gl_canon(poseidon_sbox(x)); }
 
-__device__ __forceinline__ void mds_canon(u64 s[12]) {
+// Exact integer accumulator for recompositions sum_j limb_j * B^j (limbs are arbitrary field elements on the coset, < 2^64):
+// Horner steps are a 128-bit shift-and-add (6 instructions) instead of two modular doublings and a modular add (24);
+// one reduction at the end.  The caller keeps the running value below 2^128 (bounds at each use).
+struct acc128 { u64 lo, hi; };
+GL_HD void acc128_shl_add(acc128 &A, int sh, u64 x) {            // A = (A << sh) + x
+    A.hi = (A.hi << sh) | (A.lo >> (64 - sh)); A.lo <<= sh;
+    u64 l = A.lo + x; A.hi += l < x; A.lo = l;
+}
+GL_HD void acc128_add_shifted(acc128 &A, u64 x, int sh) {       // A += x << sh   (0 <= sh < 64)
+    u64 xl = x << sh, xh = sh ? x >> (64 - sh) : 0;
+    u64 l = A.lo + xl; A.hi += xh + (l < xl); A.lo = l;
+}
+GL_HD u64 acc128_reduce(const acc128 &A) { return gl_canon(gl_reduce128_nc(A.lo, A.hi)); }
+
+GL_HD void mds_canon(u64 s[12]) {
     poseidon_mds(s);
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
@@ -87,10 +129,10 @@ __device__ __forceinline__ void mds_canon(u64 s[12]) {
 // memory, the S-box layer is a rolled loop, all 30 rounds share one MDS.  Partial rounds use the textbook form: the
 // S-box input of round r is (state[0] + RC[12r]) in both the textbook and the "fast" formulation the reference gate
 // is written in (checked in tests/test_gate_parity.py), so every constraint value is identical.
-static __device__ __noinline__ void eval_poseidon_gate_smem(const Wires &w, ConstraintSink &sink, u64 *st, const int stride) {
+GATE_NOINLINE void eval_poseidon_gate_smem(const Wires &w, ConstraintSink &sink, u64 *st, const int stride) {
     {
         u64 swap = w[24];
-        sink.push(gl_mul(swap, gl_sub(swap, 1)));
+        sink.push(gl_mul_nc(swap, gl_sub(swap, 1)));
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             u64 lhs = w[i], rhs = w[i + 4], d = w[25 + i];
@@ -102,7 +144,7 @@ static __device__ __noinline__ void eval_poseidon_gate_smem(const Wires &w, Cons
     }
     for (int r = 0; r < 30; r++) {
         const bool full = (r < 4) || (r >= 26);
-        const u64 *rc = d_POSEIDON_RC + 12 * r;
+        const u64 *rc = PT(POSEIDON_RC) + 12 * r;
         u64 s[12];
         if (full) {
             const int wbase = (r < 4) ? 29 + 12 * (r - 1) : 87 + 12 * (r - 26);
@@ -132,7 +174,7 @@ static __device__ __noinline__ void eval_poseidon_gate_smem(const Wires &w, Cons
     for (int i = 0; i < 12; i++) sink.push(gl_sub(gl_canon(st[i * stride]), w[12 + i]));
 }
 
-static __device__ __noinline__ void eval_coset_interpolation(const GateDesc &g, const Wires &w, const u64 *weights, ConstraintSink &sink) {
+GATE_NOINLINE void eval_coset_interpolation(const GateDesc &g, const Wires &w, const u64 *weights, ConstraintSink &sink) {
     const u32 sb = g.p[0], degree = g.p[1], np = 1u << sb, n_inter = (np - 2) / (degree - 1);
     const u32 start_inter = 1 + 2 * np + 4;
     u64 shift = w[0];
@@ -151,7 +193,7 @@ static __device__ __noinline__ void eval_coset_interpolation(const GateDesc &g, 
             ev = ie; prod = ip; inter_i++; next_break += degree - 1;
         }
         alg2 term = alg_sub(sep, A2(x, 0));
-        alg2 wv = alg_scalar(__ldg(weights + i), W2(w, 1 + 2 * i));
+        alg2 wv = alg_scalar(GATE_LD(weights + i), W2(w, 1 + 2 * i));
         ev = alg_add(alg_mul(ev, term), alg_mul(wv, prod));
         prod = alg_mul(prod, term);
         x = gl_mul(x, gen);
@@ -159,39 +201,80 @@ static __device__ __noinline__ void eval_coset_interpolation(const GateDesc &g, 
     alg2 d = alg_sub(W2(w, 1 + 2 * np + 2), ev); sink.push(d.a); sink.push(d.b);
 }
 
+// 2-bit-limb blocks shared by the u32 gates: NB batches of 8 limb wires, columns [col, col + 8 NB), processed highest
+// limb first as the reference iterates (`.rev()`): pushes the range-check product of every limb and Horner-accumulates
+// sum_j limb_j 4^j exactly (< 2^64 * 4^16 / 3 < 2^96 per 16 limbs).  The first SPLIT batches go to `hi`, the rest to `lo`.
+// Loads are software-pipelined: the next batch of 8 columns is in flight while the current one is evaluated (the kernels
+// are otherwise latency-bound on their column walks: ncu long_scoreboard 40 %, profiles/ncu_gates_r02_v2.jsonl); the batch
+// loop stays rolled (two batches per iteration) so that the kernel body fits the instruction cache.
+GL_HD void limbs4_batch(const u64 (&L)[8], ConstraintSink &sink, acc128 &A) {
+#pragma unroll
+    for (int k = 7; k >= 0; k--) { sink.push(range_prod4(L[k])); acc128_shl_add(A, 2, L[k]); }
+}
+template <int NB, int SPLIT>
+GL_HD void limbs4_blocks(const Wires &w, u32 col, ConstraintSink &sink, acc128 &hi, acc128 &lo) {
+    static_assert(NB % 2 == 0 && SPLIT % 2 == 0, "batches are processed in pairs");
+    u64 A[8], B[8];
+    acc128 acc = {0, 0};
+    w.load<8>(col + 8 * (NB - 1), A);
+#pragma unroll 1
+    for (int b = NB - 1; b >= 1; b -= 2) {
+        w.load<8>(col + 8 * (b - 1), B);
+        limbs4_batch(A, sink, acc);
+        if (b >= 2) w.load<8>(col + 8 * (b - 2), A);
+        limbs4_batch(B, sink, acc);
+        if (SPLIT && b - 1 == NB - SPLIT) { hi = acc; acc.lo = 0; acc.hi = 0; }
+    }
+    lo = acc;
+}
+
 // consts: constant columns AFTER the selector prefix.  KIND is a compile-time constant: every gate kind gets its own
 // small kernel (k_gate<KIND> in plonk.cu) -- a monolithic all-gates kernel (26 k instructions) was instruction-fetch bound.
 template <int KIND>
-__device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, const Wires &w, const u64 *pi_hash,
-                                          const u64 *extra, ConstraintSink &sink, u64 *smem_state, int smem_stride) {
+GL_HD void eval_gate(const GateDesc &g, const Wires &c, const Wires &w, const u64 *pi_hash,
+                     const u64 *extra, ConstraintSink &sink, u64 *smem_state, int smem_stride) {
     switch (KIND) {
     case G_NOOP: break;
     case G_CONSTANT: for (u32 i = 0; i < g.p[0]; i++) sink.push(gl_sub(c[i], w[i])); break;
     case G_PUBLIC_INPUT: for (u32 i = 0; i < 4; i++) sink.push(gl_sub(w[i], pi_hash[i])); break;
     case G_ARITHMETIC: {
         u64 c0 = c[0], c1 = c[1];
-        for (u32 i = 0; i < g.p[0]; i++)
-            sink.push(gl_sub(w[4 * i + 3], gl_add(gl_mul(gl_mul(w[4 * i], w[4 * i + 1]), c0), gl_mul(w[4 * i + 2], c1))));
+        for (u32 i = 0; i < g.p[0]; i++) {
+            u64 x[4]; w.load<4>(4 * i, x);
+            sink.push(gl_sub(x[3], gl_add(gl_mul(gl_mul(x[0], x[1]), c0), gl_mul(x[2], c1))));
+        }
         break; }
     case G_ARITHMETIC_EXT: {
         u64 c0 = c[0], c1 = c[1];
         for (u32 i = 0; i < g.p[0]; i++) {
-            alg2 comp = alg_add(alg_scalar(c1, W2(w, 8 * i + 4)), alg_scalar(c0, alg_mul(W2(w, 8 * i), W2(w, 8 * i + 2))));
-            alg2 d = alg_sub(W2(w, 8 * i + 6), comp); sink.push(d.a); sink.push(d.b);
+            u64 x[8]; w.load<8>(8 * i, x);
+            alg2 comp = alg_add(alg_scalar(c1, A2(x[4], x[5])), alg_scalar(c0, alg_mul(A2(x[0], x[1]), A2(x[2], x[3]))));
+            alg2 d = alg_sub(A2(x[6], x[7]), comp); sink.push(d.a); sink.push(d.b);
         }
         break; }
     case G_MUL_EXT: {
         u64 c0 = c[0];
         for (u32 i = 0; i < g.p[0]; i++) {
-            alg2 d = alg_sub(W2(w, 6 * i + 4), alg_scalar(c0, alg_mul(W2(w, 6 * i), W2(w, 6 * i + 2)))); sink.push(d.a); sink.push(d.b);
+            u64 x[6]; w.load<6>(6 * i, x);
+            alg2 d = alg_sub(A2(x[4], x[5]), alg_scalar(c0, alg_mul(A2(x[0], x[1]), A2(x[2], x[3])))); sink.push(d.a); sink.push(d.b);
         }
         break; }
     case G_BASE_SUM: {
         const u32 n = g.p[0], base = g.p[1];
-        u64 acc = 0;
-        for (int i = (int)n - 1; i >= 0; i--) acc = gl_add(gl_mul(acc, base), w[1 + i]);
-        sink.push(gl_sub(acc, w[0]));
-        for (u32 i = 0; i < n; i++) sink.push(base == 2 ? range_prod2(w[1 + i]) : range_prod_n(w[1 + i], (int)base));
+        if (base == 2 && n <= 64) {
+            // sum_i limb_i 2^i as an exact integer (< 2^64 * 2^n: split at 32 limbs so that each half stays < 2^96)
+            acc128 hi = {0, 0}, lo = {0, 0};
+            for (int i = (int)n - 1; i >= 32; i--) acc128_shl_add(hi, 1, w[1 + i]);
+            for (int i = (int)(n < 32 ? n : 32) - 1; i >= 0; i--) acc128_shl_add(lo, 1, w[1 + i]);
+            u64 acc = gl_add(gl_mul(acc128_reduce(hi), 1ULL << 32), acc128_reduce(lo));
+            sink.push(gl_sub(acc, w[0]));
+            for (u32 i = 0; i < n; i++) sink.push(range_prod2(w[1 + i]));
+        } else {
+            u64 acc = 0;
+            for (int i = (int)n - 1; i >= 0; i--) acc = gl_add(gl_mul(acc, base), w[1 + i]);
+            sink.push(gl_sub(acc, w[0]));
+            for (u32 i = 0; i < n; i++) sink.push(base == 2 ? range_prod2(w[1 + i]) : range_prod_n(w[1 + i], (int)base));
+        }
         break; }
     case G_REDUCING: case G_REDUCING_EXT: {
         const u32 n = g.p[0]; const bool ext = KIND == G_REDUCING_EXT;
@@ -210,7 +293,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
         for (u32 cp = 0; cp < copies; cp++) {
             const u32 base = (2 + vec) * cp;
             u64 b[6];
-            for (u32 i = 0; i < bits && i < 6; i++) { b[i] = w[routed + cp * bits + i]; sink.push(gl_sub(gl_mul(b[i], b[i]), b[i])); }
+            for (u32 i = 0; i < bits && i < 6; i++) { b[i] = w[routed + cp * bits + i]; sink.push(range_prod2(b[i])); }
             u64 rec = 0;
             for (int i = (int)bits - 1; i >= 0; i--) rec = gl_add(gl_add(rec, rec), b[i]);
             sink.push(gl_sub(rec, w[base]));
@@ -241,77 +324,106 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
     case G_U32_ARITHMETIC: {
         const u32 n = g.p[0];
         for (u32 i = 0; i < n; i++) {
-            u64 m0 = w[6 * i], m1 = w[6 * i + 1], ad = w[6 * i + 2], lo = w[6 * i + 3], hi = w[6 * i + 4], inv = w[6 * i + 5];
-            u64 comp = gl_add(gl_mul(m0, m1), ad);
-            sink.push(gl_mul(gl_sub(gl_mul(inv, gl_sub(0xFFFFFFFFULL, hi)), 1), lo));
-            sink.push(gl_sub(gl_add(gl_mul(hi, 1ULL << 32), lo), comp));
-            u64 cl = 0, ch = 0;
-            for (int j = 31; j >= 0; j--) {
-                u64 limb = w[6 * n + 32 * i + j];
-                sink.push(range_prod4(limb));
-                if (j < 16) cl = gl_add(gl_x4(cl), limb); else ch = gl_add(gl_x4(ch), limb);
-            }
-            sink.push(gl_sub(cl, lo)); sink.push(gl_sub(ch, hi));
+            u64 r[6]; w.load<6>(6 * i, r);              // m0, m1, addend, out_lo, out_hi, inverse
+            u64 comp = gl_add(gl_mul(r[0], r[1]), r[2]);
+            sink.push(gl_mul_nc(gl_sub(gl_mul(r[5], gl_sub(0xFFFFFFFFULL, r[4])), 1), r[3]));
+            sink.push(gl_sub(gl_add(gl_mul(r[4], 1ULL << 32), r[3]), comp));
+            acc128 ch = {0, 0}, cl = {0, 0};
+            limbs4_blocks<4, 2>(w, 6 * n + 32 * i, sink, ch, cl);
+            sink.push(gl_sub(acc128_reduce(cl), r[3])); sink.push(gl_sub(acc128_reduce(ch), r[4]));
         }
         break; }
     case G_U32_ADD_MANY: {
         const u32 na = g.p[0], n = g.p[1], r = na + 3;
         for (u32 i = 0; i < n; i++) {
-            u64 comp = 0;
-            for (u32 j = 0; j <= na; j++) comp = gl_add(comp, w[r * i + j]);
+            acc128 sum = {0, 0};                         // <= 17 addends < 2^64 each
+            for (u32 j = 0; j <= na; j++) acc128_add_shifted(sum, w[r * i + j], 0);
             u64 res = w[r * i + na + 1], carry = w[r * i + na + 2];
-            sink.push(gl_sub(gl_add(gl_mul(carry, 1ULL << 32), res), comp));
-            u64 cr = 0, cc = 0;
-            for (int j = 17; j >= 0; j--) {
-                u64 limb = w[r * n + 18 * i + j];
-                sink.push(range_prod4(limb));
-                if (j < 16) cr = gl_add(gl_x4(cr), limb); else cc = gl_add(gl_x4(cc), limb);
-            }
-            sink.push(gl_sub(cr, res)); sink.push(gl_sub(cc, carry));
+            sink.push(gl_sub(gl_add(gl_mul(carry, 1ULL << 32), res), acc128_reduce(sum)));
+            acc128 cc = {0, 0}, cr = {0, 0};
+            const u32 lb = r * n + 18 * i;
+            { u64 L[2]; w.load<2>(lb + 16, L);
+              sink.push(range_prod4(L[1])); acc128_shl_add(cc, 2, L[1]); sink.push(range_prod4(L[0])); acc128_shl_add(cc, 2, L[0]); }
+            { acc128 unused = {0, 0}; limbs4_blocks<2, 0>(w, lb, sink, unused, cr); }
+            sink.push(gl_sub(acc128_reduce(cr), res)); sink.push(gl_sub(acc128_reduce(cc), carry));
         }
         break; }
     case G_U32_SUBTRACTION: {
         const u32 n = g.p[0];
         for (u32 i = 0; i < n; i++) {
-            u64 x = w[5 * i], y = w[5 * i + 1], bi = w[5 * i + 2], res = w[5 * i + 3], bo = w[5 * i + 4];
-            sink.push(gl_sub(res, gl_add(gl_sub(gl_sub(x, y), bi), gl_mul(1ULL << 32, bo))));
-            u64 cl = 0;
-            for (int j = 15; j >= 0; j--) { u64 limb = w[5 * n + 16 * i + j]; sink.push(range_prod4(limb)); cl = gl_add(gl_x4(cl), limb); }
-            sink.push(gl_sub(cl, res));
-            sink.push(gl_mul(bo, gl_sub(1, bo)));
+            u64 r[5]; w.load<5>(5 * i, r);              // x, y, borrow_in, out, borrow_out
+            sink.push(gl_sub(r[3], gl_add(gl_sub(gl_sub(r[0], r[1]), r[2]), gl_mul(1ULL << 32, r[4]))));
+            acc128 cl = {0, 0}, unused = {0, 0};
+            limbs4_blocks<2, 0>(w, 5 * n + 16 * i, sink, unused, cl);
+            sink.push(gl_sub(acc128_reduce(cl), r[3]));
+            sink.push(gl_mul_nc(r[4], gl_sub(1, r[4])));
         }
         break; }
     case G_U32_RANGE_CHECK: {
         const u32 n = g.p[0];
         for (u32 i = 0; i < n; i++) {
-            u64 acc = 0;
-            for (int j = 15; j >= 0; j--) acc = gl_add(gl_x4(acc), w[n + 16 * i + j]);
-            sink.push(gl_sub(acc, w[i]));
-            for (int j = 0; j < 16; j++) sink.push(range_prod4(w[n + 16 * i + j]));
+            u64 L[16]; w.load<16>(n + 16 * i, L);
+            acc128 acc = {0, 0};
+#pragma unroll
+            for (int j = 15; j >= 0; j--) acc128_shl_add(acc, 2, L[j]);
+            sink.push(gl_sub(acc128_reduce(acc), w[i]));
+#pragma unroll
+            for (int j = 0; j < 16; j++) sink.push(range_prod4(L[j]));
         }
         break; }
     case G_U32_INTERLEAVE: {
         const u32 n = g.p[0];
         for (u32 i = 0; i < n; i++) {
-            u64 cx = 0, ci = 0;
-            for (int j = 0; j < 32; j++) { u64 b = w[2 * n + 32 * i + j]; cx = gl_add(gl_dbl(cx), b); ci = gl_add(gl_x4(ci), b); }
-            sink.push(gl_sub(cx, w[2 * i])); sink.push(gl_sub(ci, w[2 * i + 1]));
-            for (int j = 0; j < 32; j++) sink.push(range_prod2(w[2 * n + 32 * i + j]));
+            // one pass over the 32 bit wires: the two recomposition constraints come first in the reference's order, so the
+            // range checks are pushed at their explicit indices and the recompositions afterwards
+            acc128 cx = {0, 0}, ci = {0, 0};             // cx < 2^64 * 2^32, ci < 2^64 * 4^32 / 3 < 2^127
+            const u32 lb = 2 * n + 32 * i, at0 = sink.idx;
+            u64 A[8], B[8];
+            w.load<8>(lb, A);
+#pragma unroll 1
+            for (int jb = 0; jb < 32; jb += 16) {
+                w.load<8>(lb + jb + 8, B);
+#pragma unroll
+                for (int k = 0; k < 8; k++) { acc128_shl_add(cx, 1, A[k]); acc128_shl_add(ci, 2, A[k]); sink.push_at(range_prod2(A[k]), at0 + 2 + jb + k); }
+                if (jb == 0) w.load<8>(lb + 16, A);
+#pragma unroll
+                for (int k = 0; k < 8; k++) { acc128_shl_add(cx, 1, B[k]); acc128_shl_add(ci, 2, B[k]); sink.push_at(range_prod2(B[k]), at0 + 10 + jb + k); }
+            }
+            sink.push_at(gl_sub(acc128_reduce(cx), w[2 * i]), at0); sink.push_at(gl_sub(acc128_reduce(ci), w[2 * i + 1]), at0 + 1);
+            sink.idx = at0 + 34;
         }
         break; }
     case G_UNINTERLEAVE_U32: case G_UNINTERLEAVE_B32: {
         const u32 n = g.p[0]; const bool b32 = KIND == G_UNINTERLEAVE_B32;
         for (u32 i = 0; i < n; i++) {
-            u64 ci = 0, ce = 0, co = 0;
-            for (int j = 0; j < 64; j++) {
-                u64 b = w[3 * n + 64 * i + j];
-                ci = gl_add(gl_add(ci, ci), b);
-                int jj = j >> 1;
-                u64 coeff = b32 ? (1ULL << (2 * (31 - jj))) : (1ULL << (31 - jj));
-                if (j & 1) co = gl_add(co, gl_mul(coeff, b)); else ce = gl_add(ce, gl_mul(coeff, b));
+            // x_interleaved = sum_j b_j 2^(63-j): two exact halves of 32 bits each (< 2^96), joined modularly;
+            // evens / odds: sum over 32 bits with weights 2^(31-jj) (u32) or 4^(31-jj) (b32): < 2^64 * 2^63 exact.
+            // One pass over the 64 bit wires, range checks pushed at their explicit indices (after the three recompositions).
+            acc128 ih = {0, 0}, il = {0, 0}, ce = {0, 0}, co = {0, 0};
+            const u32 lb = 3 * n + 64 * i, at0 = sink.idx;
+            u64 A[8], B[8];
+            w.load<8>(lb, A);
+#pragma unroll 1
+            for (int jb = 0; jb < 64; jb += 16) {
+                w.load<8>(lb + jb + 8, B);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (jb < 32) acc128_shl_add(ih, 1, A[k]); else acc128_shl_add(il, 1, A[k]);
+                    if (k & 1) acc128_shl_add(co, b32 ? 2 : 1, A[k]); else acc128_shl_add(ce, b32 ? 2 : 1, A[k]);
+                    sink.push_at(range_prod2(A[k]), at0 + 3 + jb + k);
+                }
+                if (jb + 16 < 64) w.load<8>(lb + jb + 16, A);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (jb < 32) acc128_shl_add(ih, 1, B[k]); else acc128_shl_add(il, 1, B[k]);
+                    if (k & 1) acc128_shl_add(co, b32 ? 2 : 1, B[k]); else acc128_shl_add(ce, b32 ? 2 : 1, B[k]);
+                    sink.push_at(range_prod2(B[k]), at0 + 11 + jb + k);
+                }
             }
-            sink.push(gl_sub(ci, w[3 * i])); sink.push(gl_sub(ce, w[3 * i + 1])); sink.push(gl_sub(co, w[3 * i + 2]));
-            for (int j = 0; j < 64; j++) sink.push(range_prod2(w[3 * n + 64 * i + j]));
+            u64 cint = gl_add(gl_mul(acc128_reduce(ih), 1ULL << 32), acc128_reduce(il));
+            sink.push_at(gl_sub(cint, w[3 * i]), at0); sink.push_at(gl_sub(acc128_reduce(ce), w[3 * i + 1]), at0 + 1);
+            sink.push_at(gl_sub(acc128_reduce(co), w[3 * i + 2]), at0 + 2);
+            sink.idx = at0 + 67;
         }
         break; }
     case G_COMPARISON: {
@@ -325,7 +437,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
             sink.push(range_prod_n(f, 1 << cb)); sink.push(range_prod_n(s, 1 << cb));
             u64 diff = gl_sub(s, f), dummy = w[4 + 2 * nc + i], eq = w[4 + 3 * nc + i];
             sink.push(gl_sub(gl_mul(diff, dummy), gl_sub(1, eq)));
-            sink.push(gl_mul(eq, diff));
+            sink.push(gl_mul_nc(eq, diff));
             u64 inter = w[4 + 4 * nc + i];
             sink.push(gl_sub(inter, gl_mul(eq, msd)));
             msd = gl_add(inter, gl_mul(gl_sub(1, eq), diff));
@@ -334,7 +446,7 @@ __device__ __forceinline__ void eval_gate(const GateDesc &g, const Wires &c, con
         sink.push(gl_sub(msdw, msd));
         u64 comb = 0;
         for (int i = (int)cb; i >= 0; i--) comb = gl_add(gl_add(comb, comb), w[4 + 5 * nc + i]);
-        for (u32 i = 0; i <= cb; i++) { u64 b = w[4 + 5 * nc + i]; sink.push(gl_mul(b, gl_sub(1, b))); }
+        for (u32 i = 0; i <= cb; i++) { u64 b = w[4 + 5 * nc + i]; sink.push(gl_mul_nc(b, gl_sub(1, b))); }
         sink.push(gl_sub(gl_add(1ULL << cb, msdw), comb));
         sink.push(gl_sub(w[2], w[4 + 5 * nc + cb]));
         break; }

@@ -41,15 +41,31 @@ GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 
 GL_HD void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
 #ifdef __CUDA_ARCH__
-    // 4 x IMAD.WIDE.U32 with the 64-bit addend folded in + one 64-bit add (the 32x32->64 multiplier is the
-    // scarce unit on sm_100a: 25 /clk/SM, see profiles/int_peak_r01.jsonl)
-    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    const u64 p00 = (u64)a0 * b0;
-    const u64 t = (u64)a0 * b1 + (p00 >> 32);          // cannot overflow: (2^32-1)^2 + 2^32-1 < 2^64
-    const u64 u = (u64)a1 * b0 + (u32)t;
-    const u64 h = (u64)a1 * b1 + (t >> 32);
-    hi = h + (u >> 32);
-    lo = (u << 32) | (u32)p00;
+    // Four INDEPENDENT IMAD.WIDE.U32 and a six-instruction carry chain.  (A chained form -- each product added onto the
+    // shifted previous one -- needs its 64-bit addend pair rebuilt before every IMAD.WIDE: two extra moves per product in
+    // SASS.  The 32x32->64 multiplier is the scarce unit on sm_100a: 25 /clk/SM, profiles/int_peak_r01.jsonl.)
+    u32 x0, x1, x2, x3;
+    asm("{\n\t"
+        ".reg .u64 p00, p01, p10, p11;\n\t"
+        ".reg .u32 a0, a1, b0, b1, l01, h01, l10, h10, l11, h11, h00, m0, m1, m2;\n\t"
+        "mov.b64 {a0, a1}, %4;\n\t"
+        "mov.b64 {b0, b1}, %5;\n\t"
+        "mul.wide.u32 p00, a0, b0;\n\t"
+        "mul.wide.u32 p01, a0, b1;\n\t"
+        "mul.wide.u32 p10, a1, b0;\n\t"
+        "mul.wide.u32 p11, a1, b1;\n\t"
+        "mov.b64 {%0, h00}, p00;\n\t"
+        "mov.b64 {l01, h01}, p01;\n\t"
+        "mov.b64 {l10, h10}, p10;\n\t"
+        "mov.b64 {l11, h11}, p11;\n\t"
+        "add.cc.u32 m0, l01, l10;\n\t"          // mid = p01 + p10 (65 bits: m2:m1:m0)
+        "addc.cc.u32 m1, h01, h10;\n\t"
+        "addc.u32 m2, 0, 0;\n\t"
+        "add.cc.u32 %1, h00, m0;\n\t"
+        "addc.cc.u32 %2, l11, m1;\n\t"
+        "addc.u32 %3, h11, m2;\n\t"
+        "}" : "=r"(x0), "=&r"(x1), "=&r"(x2), "=&r"(x3) : "l"(a), "l"(b));
+    lo = ((u64)x1 << 32) | x0; hi = ((u64)x3 << 32) | x2;
 #else
     unsigned __int128 p = (unsigned __int128)a * b; lo = (u64)p; hi = (u64)(p >> 64);
 #endif

@@ -82,3 +82,45 @@ struct Challenger {
     gl2 get_ext() { gl2 r; r.a = get(); r.b = get(); return r; }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// C::Hasher on the host (both hashers): hash_or_noop / two_to_one, and the circuit digest of CircuitBuilder::build
+//   circuit_digest = H(constants_sigmas_cap || H_pad(domain_separator = []) || degree_bits)
+// (upstream plonky2 plonk/circuit_builder.rs, not vendored; pinned by the golden verifier_data.json of the three final
+// proofs for the BN128 hasher: tests/test_oracle_verifier.py, tests/test_product_verifier.py)
+// ------------------------------------------------------------------------------------------------
+static inline void hash_or_noop(const u64 *x, size_t n, int hasher, u64 out[4]) {
+    if (hasher == HASHER_BN254) {
+        if (n <= 3) { for (int i = 0; i < 4; i++) out[i] = (size_t)i < n ? x[i] : 0; return; }
+        fr_t s[4]; for (int i = 0; i < 4; i++) for (int k = 0; k < 4; k++) s[i].v[k] = 0;
+        for (size_t i = 0; i < n; i += 9) {
+            size_t m = n - i < 9 ? n - i : 9;
+            for (size_t j = 0; j < m; j += 3) { u64 l[4] = {x[i + j], j + 1 < m ? x[i + j + 1] : 0, j + 2 < m ? x[i + j + 2] : 0, 0}; s[j / 3 + 1] = fr_from_canonical(l); }
+            bn254_permute(s);
+        }
+        fr_to_canonical(s[0], out);
+    } else {
+        if (n <= 4) { for (int i = 0; i < 4; i++) out[i] = (size_t)i < n ? x[i] : 0; return; }
+        poseidon_hash_no_pad_host(x, n, out);
+    }
+}
+static inline void two_to_one(const u64 l[4], const u64 r[4], int hasher, u64 out[4]) {
+    if (hasher == HASHER_BN254) bn254_two_to_one(l, r, out); else poseidon_two_to_one(l, r, out);
+}
+
+static inline void circuit_digest_host(const u64 *cap, size_t ncap, u32 degree_bits, int hasher, u64 out[4]) {
+    std::vector<u64> parts;
+    if (hasher == HASHER_BN254) {
+        u64 pad[9] = {1, 0, 0, 0, 0, 0, 0, 0, 1}, dom[4], v[5];      // hash_pad([]): [1], zero-fill to 8, closing 1 (rate 9)
+        hash_or_noop(pad, 9, hasher, dom);
+        for (size_t i = 0; i < ncap; i++) { bn254_to_vec_host(cap + 4 * i, v); parts.insert(parts.end(), v, v + 5); }
+        bn254_to_vec_host(dom, v); parts.insert(parts.end(), v, v + 5);
+    } else {
+        u64 pad[8] = {1, 0, 0, 0, 0, 0, 0, 1}, dom[4];               // rate 8
+        hash_or_noop(pad, 8, hasher, dom);
+        parts.assign(cap, cap + 4 * ncap);
+        parts.insert(parts.end(), dom, dom + 4);
+    }
+    parts.push_back(degree_bits);
+    hash_or_noop(parts.data(), parts.size(), hasher, out);
+}

@@ -164,6 +164,13 @@ void ntt_dif(const NttTables &T, const u64 *in, size_t in_stride, bool in_bitrev
     if (L == 0) {   // size-1 transform: copy
         throw CudaErr{cudaErrorInvalidValue, __FILE__, __LINE__};
     }
+    // 2^16 .. 2^20 points: bulk-copy staged passes with register-resident twiddles (ntt2.cu)
+    if (ntt2_supported(L, in_stride, out_stride, rate_bits) && (in_bitrev || (rate_bits == 0 && scale == nullptr)) &&
+        (!rate_bits || out_stride == (size_t(1) << (L + rate_bits))) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+        (!scale || (uintptr_t)scale % 16 == 0)) {
+        ntt2_dif(T, in, in_stride, in_bitrev, out, out_stride, L, items, rate_bits, scale, inverse, out_mul, st);
+        return;
+    }
     // split L layers into passes: all strided passes must have S >= 16
     int npass = (L + NTT_MAX_TILE_LOG - 1) / NTT_MAX_TILE_LOG;
     std::vector<int> Bs(npass);

@@ -142,10 +142,23 @@ __global__ void __launch_bounds__(128) k_quotient_perm(QuotientArgs a) {
         u64 prev = z;
         for (u32 kk = 0; kk <= npp; kk++) {
             u64 num = 1, den = 1;
-            for (u32 j = kk * a.qdf; j < (kk + 1) * a.qdf && j < a.num_routed; j++) {
-                u64 t0 = gl_add(w[j], a.gammas[c]);
-                num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j), x))));
-                den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], cs[a.num_constants + j])));
+            const u32 j0 = kk * a.qdf;
+            if (a.qdf == 8 && j0 + 8 <= a.num_routed) {
+                // the usual chunk of 8 routed wires: 16 independent column loads in flight before the product chains start
+                u64 wv[8], sg[8];
+                w.load<8>(j0, wv); cs.load<8>(a.num_constants + j0, sg);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    u64 t0 = gl_add(wv[j], a.gammas[c]);
+                    num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j0 + j), x))));
+                    den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], sg[j])));
+                }
+            } else {
+                for (u32 j = j0; j < j0 + a.qdf && j < a.num_routed; j++) {
+                    u64 t0 = gl_add(w[j], a.gammas[c]);
+                    num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j), x))));
+                    den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], cs[a.num_constants + j])));
+                }
             }
             u64 next = kk < npp ? zs[nch + c * npp + kk] : zs_next[c];
             u64 term = gl_sub(gl_mul(prev, num), gl_mul(next, den));

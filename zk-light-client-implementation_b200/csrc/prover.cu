@@ -35,6 +35,9 @@ struct b200_circuit {
     DevBuf d_gates, d_extra, d_kis;
     DevBuf cs_coeffs, cs_lde, cs_digests, sigma_values;
     u64 digest[4];
+    std::vector<u64> cap;               // constants/sigmas cap, host copy
+    // circuit cache (b200_circuit_build): handles are reference counted, the context keeps cached circuits alive
+    int refs = 1; bool cached = false; u64 key[2] = {0, 0}; u64 last_use = 0;
 };
 
 struct Arena {      // bump allocator over one device allocation, reset per prove
@@ -427,12 +430,8 @@ int ctx_fail(b200_ctx *ctx, int code, const std::string &msg);
     } catch (const std::bad_alloc &) { return ctx_fail(ctx, B200_ERR_OOM, "host allocation failed"); \
     } catch (const std::exception &e) { return ctx_fail(ctx, B200_ERR_BAD_ARG, e.what()); }
 
-extern "C" {
-
-int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_values, const uint64_t digest[4], uint64_t *cap_out, b200_circuit **out) {
-    API_BEGIN(ctx)
-    if (!c || !cs_values || !digest || !out) throw ApiErr{B200_ERR_BAD_ARG, "b200_circuit_upload: null argument"};
-    *out = nullptr;
+// ---- shared by b200_circuit_upload and b200_circuit_build: validate `c`, parse the gate table ----
+static std::unique_ptr<b200_circuit> circuit_from_common(b200_ctx *ctx, const b200_common *c) {
     if (c->hasher > 1) throw ApiErr{B200_ERR_UNSUPPORTED, "hasher must be 0 (PoseidonGoldilocksConfig) or 1 (PoseidonBN128GoldilocksConfig)"};
     if (c->num_challenges == 0 || c->num_challenges > MAX_CHALLENGES) throw ApiErr{B200_ERR_UNSUPPORTED, "num_challenges must be 1 or 2"};
     if (c->rate_bits == 0 || c->rate_bits > 4) throw ApiErr{B200_ERR_UNSUPPORTED, "rate_bits must be in 1..4"};     // QuotientArgs::zh_ev[16]
@@ -468,33 +467,179 @@ int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_
         k->gates.push_back(g);
     }
     k->k_is.assign(c->k_is, c->k_is + c->num_routed_wires);
-    memcpy(k->digest, digest, 32);
+    return k;
+}
+// commit device-resident constants/sigmas VALUES [num_constants + num_routed][n] (consumed), derive the digest if none is given
+static void circuit_commit(b200_ctx *ctx, b200_circuit *k, DevBuf &vals, const uint64_t *digest, uint64_t *cap_out) {
     cudaStream_t st = ctx->stream;
-    const size_t n = size_t(1) << c->degree_bits, N = n << c->rate_bits;
-    const size_t cols = (size_t)c->num_constants + c->num_routed_wires;
+    const size_t n = size_t(1) << k->degree_bits, N = n << k->rate_bits;
+    const size_t cols = (size_t)k->num_constants + k->num_routed;
     k->d_gates.alloc(std::max<size_t>(1, k->gates.size()) * sizeof(GateDesc));
-    k->d_extra.alloc(std::max<size_t>(1, extra.size()) * 8);
-    k->d_kis.alloc(k->k_is.size() * 8);
+    k->d_extra.alloc(std::max<size_t>(1, k->extra.size()) * 8);
+    k->d_kis.alloc(std::max<size_t>(1, k->k_is.size()) * 8);
     CUDA_TRY(cudaMemcpyAsync(k->d_gates.p, k->gates.data(), k->gates.size() * sizeof(GateDesc), cudaMemcpyHostToDevice, st));
-    if (!extra.empty()) CUDA_TRY(cudaMemcpyAsync(k->d_extra.p, extra.data(), extra.size() * 8, cudaMemcpyHostToDevice, st));
+    if (!k->extra.empty()) CUDA_TRY(cudaMemcpyAsync(k->d_extra.p, k->extra.data(), k->extra.size() * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(k->d_kis.p, k->k_is.data(), k->k_is.size() * 8, cudaMemcpyHostToDevice, st));
-    DevBuf vals(cols * n * 8);
-    CUDA_TRY(cudaMemcpyAsync(vals.p, cs_values, cols * n * 8, cudaMemcpyHostToDevice, st));
     k->cs_coeffs.alloc(cols * n * 8); k->cs_lde.alloc(cols * N * 8);
-    size_t nd = merkle_num_u64((int)(c->degree_bits + c->rate_bits), (int)c->cap_height);
+    const size_t nd = merkle_num_u64((int)(k->degree_bits + k->rate_bits), (int)k->cap_height);
     k->cs_digests.alloc(nd * 8);
-    commit_values(ctx, vals.u(), cols, (int)c->degree_bits, (int)c->rate_bits, (int)c->cap_height, k->cs_coeffs.u(), k->cs_lde.u(), k->cs_digests.u(), (int)c->hasher);
-    k->sigma_values.alloc((size_t)c->num_routed_wires * n * 8);
-    CUDA_TRY(cudaMemcpyAsync(k->sigma_values.p, vals.u() + (size_t)c->num_constants * n, (size_t)c->num_routed_wires * n * 8, cudaMemcpyDeviceToDevice, st));
-    if (cap_out) CUDA_TRY(cudaMemcpyAsync(cap_out, k->cs_digests.u() + nd - (size_t(4) << c->cap_height), size_t(32) << c->cap_height, cudaMemcpyDeviceToHost, st));
+    commit_values(ctx, vals.u(), cols, (int)k->degree_bits, (int)k->rate_bits, (int)k->cap_height, k->cs_coeffs.u(), k->cs_lde.u(), k->cs_digests.u(), (int)k->hasher);
+    k->sigma_values.alloc((size_t)k->num_routed * n * 8);
+    CUDA_TRY(cudaMemcpyAsync(k->sigma_values.p, vals.u() + (size_t)k->num_constants * n, (size_t)k->num_routed * n * 8, cudaMemcpyDeviceToDevice, st));
+    const size_t capw = size_t(4) << k->cap_height;
+    k->cap.resize(capw);
+    CUDA_TRY(cudaMemcpyAsync(k->cap.data(), k->cs_digests.u() + nd - capw, capw * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (digest) memcpy(k->digest, digest, 32);
+    else circuit_digest_host(k->cap.data(), size_t(1) << k->cap_height, k->degree_bits, (int)k->hasher, k->digest);
+    if (cap_out) memcpy(cap_out, k->cap.data(), capw * 8);
+}
+
+// ---- CircuitBuilder::build()'s device half -------------------------------------------------------------------------
+// selector columns from the gate placement: column g holds the gate index on rows whose gate belongs to selector group g,
+// UNUSED (2^32 - 1) elsewhere (a single group: just the index); reference semantics: SURVEY.md A.2 / evaluate_gates.go:33-55
+__global__ void k_build_selectors(const u32 *__restrict__ row_gate, const u32 *__restrict__ gate_group, u32 nsel, size_t n, u64 *__restrict__ cols) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 g = row_gate[i], grp = gate_group[g];
+    for (u32 s = 0; s < nsel; s++) cols[(size_t)s * n + i] = (s == grp) ? (u64)g : (nsel > 1 ? 0xFFFFFFFFULL : 0ULL);
+}
+// sigma polynomial values: slot (col, row) -> k_is[col'] * w^row' of the NEXT wire (col', row') of its copy class
+__global__ void k_build_sigmas(const u32 *__restrict__ sigma_next, const u64 *__restrict__ kis, const u64 *__restrict__ tw, int log_n, u32 R, u64 *__restrict__ sig) {
+    const size_t n = size_t(1) << log_n, total = (size_t)R << log_n;
+    size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    const u32 nx = sigma_next[s];
+    const u32 col = nx >> log_n; const size_t row = nx & (n - 1);
+    const size_t h = n >> 1;
+    u64 x = (row < h) ? tw[h + row] : gl_neg(tw[h + (row - h)]);      // w_n^row from the twiddle table tw[h + j] = w_{2h}^j
+    sig[s] = gl_mul(kis[col], x);
+}
+// 128-bit content key of the build inputs (not cryptographic: the inputs are the caller's own circuit, not adversarial)
+static void key_mix(u64 key[2], const void *data, size_t bytes) {
+    const u64 *w = (const u64 *)data; size_t nw = bytes / 8;
+    u64 a = key[0], b = key[1];
+    for (size_t i = 0; i < nw; i++) { u64 x = w[i]; a = (a ^ x) * 0x9E3779B97F4A7C15ULL; a ^= a >> 29; b = (b + x) * 0xC2B2AE3D27D4EB4FULL; b ^= b >> 31; }
+    const uint8_t *t = (const uint8_t *)data + nw * 8;
+    for (size_t i = 0; i < bytes % 8; i++) { a = (a ^ t[i]) * 0x100000001B3ULL; b = (b + t[i]) * 0x9E3779B97F4A7C15ULL; }
+    key[0] = a; key[1] = b ^ (a >> 32);
+}
+
+void ctx_drop_circuit_cache(b200_ctx *ctx) {
+    for (b200_circuit *cc : ctx->circuit_cache) delete cc;
+    ctx->circuit_cache.clear();
+}
+
+extern "C" {
+
+int b200_circuit_upload(b200_ctx *ctx, const b200_common *c, const uint64_t *cs_values, const uint64_t *digest, uint64_t *cap_out, b200_circuit **out) {
+    API_BEGIN(ctx)
+    if (!c || !cs_values || !out) throw ApiErr{B200_ERR_BAD_ARG, "b200_circuit_upload: null argument"};
+    *out = nullptr;
+    std::unique_ptr<b200_circuit> k = circuit_from_common(ctx, c);
+    const size_t n = size_t(1) << c->degree_bits;
+    const size_t cols = (size_t)c->num_constants + c->num_routed_wires;
+    DevBuf vals(cols * n * 8);
+    CUDA_TRY(cudaMemcpyAsync(vals.p, cs_values, cols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    circuit_commit(ctx, k.get(), vals, digest, cap_out);
     *out = k.release();
     return B200_OK;
     API_END(ctx)
 }
 
+int b200_circuit_build(b200_ctx *ctx, const b200_common *c, const uint32_t *row_gate, const uint64_t *gate_constants, const uint32_t *sigma_next,
+                       uint64_t *cap_out, uint64_t *digest_out, int *cache_hit, b200_circuit **out) {
+    API_BEGIN(ctx)
+    if (!c || !row_gate || !sigma_next || !out) throw ApiErr{B200_ERR_BAD_ARG, "b200_circuit_build: null argument"};
+    *out = nullptr;
+    if (c->num_constants < c->num_selector_groups) throw ApiErr{B200_ERR_BAD_ARG, "num_constants smaller than the number of selector groups"};
+    const u32 ngc = c->num_constants - c->num_selector_groups;
+    if (ngc && !gate_constants) throw ApiErr{B200_ERR_BAD_ARG, "b200_circuit_build: gate constants missing"};
+    if (c->degree_bits > 26) throw ApiErr{B200_ERR_BAD_ARG, "degree_bits out of range"};
+    const size_t n = size_t(1) << c->degree_bits;
+    // ---- cache lookup: same gate table, placement, constants and routing => same CircuitData (recursion.rs:36-96 rebuilds
+    // an identical recursion circuit on every one of its k + 55 calls) ----
+    u64 key[2] = {0x243F6A8885A308D3ULL, 0x13198A2E03707344ULL};
+    {
+        u32 hdr[16] = {c->num_wires, c->num_routed_wires, c->num_constants, c->num_challenges, c->degree_bits, c->rate_bits, c->cap_height,
+                       c->proof_of_work_bits, c->num_query_rounds, c->quotient_degree_factor, c->num_partial_products, c->num_gate_constraints,
+                       c->num_public_inputs, c->hasher, c->num_gates, c->num_selector_groups};
+        key_mix(key, hdr, sizeof hdr);
+        key_mix(key, c->reduction_arity_bits, sizeof(u32) * std::min<u32>(c->num_reduction_arity_bits, 16));
+        for (u32 i = 0; i < c->num_gates; i++) if (c->gate_ids[i]) key_mix(key, c->gate_ids[i], strlen(c->gate_ids[i]));
+        key_mix(key, c->selector_indices, sizeof(u32) * c->num_gates);
+        key_mix(key, c->group_starts, sizeof(u32) * c->num_selector_groups); key_mix(key, c->group_ends, sizeof(u32) * c->num_selector_groups);
+        key_mix(key, c->k_is, 8 * (size_t)c->num_routed_wires);
+        key_mix(key, row_gate, 4 * n);
+        if (ngc) key_mix(key, gate_constants, 8 * n * ngc);
+        key_mix(key, sigma_next, 4 * n * c->num_routed_wires);
+    }
+    ctx->cache_tick++;
+    for (b200_circuit *cc : ctx->circuit_cache) if (cc->key[0] == key[0] && cc->key[1] == key[1]) {
+        cc->refs++; cc->last_use = ctx->cache_tick; ctx->cache_hits++;
+        if (cap_out) memcpy(cap_out, cc->cap.data(), cc->cap.size() * 8);
+        if (digest_out) memcpy(digest_out, cc->digest, 32);
+        if (cache_hit) *cache_hit = 1;
+        *out = cc;
+        return B200_OK;
+    }
+    ctx->cache_misses++;
+    if (cache_hit) *cache_hit = 0;
+    std::unique_ptr<b200_circuit> k = circuit_from_common(ctx, c);
+    for (u32 i = 0; i < n; i++) if (row_gate[i] >= c->num_gates) throw ApiErr{B200_ERR_BAD_ARG, "row_gate entry out of range"};
+    cudaStream_t st = ctx->stream;
+    const u32 R = c->num_routed_wires, nsel = c->num_selector_groups;
+    if (((u64)R << c->degree_bits) > 0xFFFFFFFFULL) throw ApiErr{B200_ERR_UNSUPPORTED, "routed slots do not fit 32-bit indices"};
+    ntt_tables_ensure(ctx->tw, (int)c->degree_bits + (int)c->rate_bits, st);
+    const size_t cols = (size_t)c->num_constants + R;
+    DevBuf vals(cols * n * 8), d_row(4 * n), d_grp(4 * std::max<u32>(1, c->num_gates)), d_next(4 * n * R), d_kis(8 * std::max<u32>(1, R));
+    CUDA_TRY(cudaMemcpyAsync(d_row.p, row_gate, 4 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_grp.p, c->selector_indices, 4 * (size_t)c->num_gates, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_next.p, sigma_next, 4 * n * R, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_kis.p, c->k_is, 8 * (size_t)R, cudaMemcpyHostToDevice, st));
+    if (ngc) CUDA_TRY(cudaMemcpyAsync(vals.u() + (size_t)nsel * n, gate_constants, 8 * n * ngc, cudaMemcpyHostToDevice, st));
+    {
+        PhaseTimer t(ctx, "build_polys");
+        k_build_selectors<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const u32 *)d_row.p, (const u32 *)d_grp.p, nsel, n, vals.u());
+        LAUNCHED(1);
+        k_build_sigmas<<<(unsigned)((n * R + 255) / 256), 256, 0, st>>>((const u32 *)d_next.p, d_kis.u(), ctx->tw.fwd, (int)c->degree_bits, R, vals.u() + (size_t)c->num_constants * n);
+        LAUNCHED(1);
+    }
+    circuit_commit(ctx, k.get(), vals, nullptr, cap_out);
+    if (digest_out) memcpy(digest_out, k->digest, 32);
+    // ---- insert into the cache (the cache holds one reference); evict unreferenced entries beyond the capacity, oldest first
+    k->cached = true; k->key[0] = key[0]; k->key[1] = key[1]; k->last_use = ctx->cache_tick; k->refs = 2;
+    b200_circuit *raw = k.release();
+    ctx->circuit_cache.push_back(raw);
+    while (ctx->circuit_cache.size() > 8) {
+        size_t victim = ctx->circuit_cache.size();
+        for (size_t i = 0; i < ctx->circuit_cache.size(); i++)
+            if (ctx->circuit_cache[i]->refs == 1 && (victim == ctx->circuit_cache.size() || ctx->circuit_cache[i]->last_use < ctx->circuit_cache[victim]->last_use)) victim = i;
+        if (victim == ctx->circuit_cache.size()) break;             // everything is in use
+        delete ctx->circuit_cache[victim];
+        ctx->circuit_cache.erase(ctx->circuit_cache.begin() + victim);
+    }
+    *out = raw;
+    return B200_OK;
+    API_END(ctx)
+}
+
+int b200_circuit_digest(uint32_t hasher, const uint64_t *cap, uint32_t cap_height, uint32_t degree_bits, uint64_t out[4]) {
+    if (hasher > 1 || !cap || !out || cap_height > 16) return B200_ERR_BAD_ARG;
+    circuit_digest_host(cap, size_t(1) << cap_height, degree_bits, (int)hasher, out);
+    return B200_OK;
+}
+
+int b200_ctx_cache_stats(const b200_ctx *ctx, uint64_t *hits, uint64_t *misses, uint64_t *entries) {
+    if (!ctx) return B200_ERR_BAD_ARG;
+    if (hits) *hits = ctx->cache_hits; if (misses) *misses = ctx->cache_misses; if (entries) *entries = ctx->circuit_cache.size();
+    return B200_OK;
+}
+
+
 void b200_circuit_free(b200_circuit *c) {
     if (!c) return;
+    if (c->cached) { if (c->refs > 1) c->refs--; return; }       // the context's cache keeps it (freed with the context or on eviction)
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
     delete c;

@@ -26,24 +26,6 @@ struct H4 { u64 w[4]; };
 struct QueryStep { std::vector<gl2> evals; std::vector<H4> sib; };
 struct QueryRound { std::vector<std::vector<u64>> leaf; std::vector<std::vector<H4>> sib; std::vector<QueryStep> steps; };
 
-static void hash_or_noop(const u64 *x, size_t n, int hasher, u64 out[4]) {
-    if (hasher == HASHER_BN254) {
-        if (n <= 3) { for (int i = 0; i < 4; i++) out[i] = (size_t)i < n ? x[i] : 0; return; }
-        fr_t s[4]; for (int i = 0; i < 4; i++) for (int k = 0; k < 4; k++) s[i].v[k] = 0;
-        for (size_t i = 0; i < n; i += 9) {
-            size_t m = n - i < 9 ? n - i : 9;
-            for (size_t j = 0; j < m; j += 3) { u64 l[4] = {x[i + j], j + 1 < m ? x[i + j + 1] : 0, j + 2 < m ? x[i + j + 2] : 0, 0}; s[j / 3 + 1] = fr_from_canonical(l); }
-            bn254_permute(s);
-        }
-        fr_to_canonical(s[0], out);
-    } else {
-        if (n <= 4) { for (int i = 0; i < 4; i++) out[i] = (size_t)i < n ? x[i] : 0; return; }
-        poseidon_hash_no_pad_host(x, n, out);
-    }
-}
-static void two_to_one(const u64 l[4], const u64 r[4], int hasher, u64 out[4]) {
-    if (hasher == HASHER_BN254) bn254_two_to_one(l, r, out); else poseidon_two_to_one(l, r, out);
-}
 static void verify_merkle(const u64 *leaf, size_t n, size_t index, const std::vector<H4> &sib, const u64 *cap, size_t cap_len, int hasher) {
     u64 d[4]; hash_or_noop(leaf, n, hasher, d);
     for (auto &s : sib) { u64 o[4]; if (index & 1) two_to_one(s.w, d, hasher, o); else two_to_one(d, s.w, hasher, o); memcpy(d, o, 32); index >>= 1; }
