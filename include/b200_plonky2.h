@@ -121,6 +121,16 @@ int b200_circuit_build(b200_ctx *ctx, const b200_common *common, const uint32_t 
 int b200_circuit_digest(uint32_t hasher, const uint64_t *cap, uint32_t cap_height, uint32_t degree_bits, uint64_t out[4]);
 int b200_ctx_cache_stats(const b200_ctx *ctx, uint64_t *hits, uint64_t *misses, uint64_t *entries);
 
+/* ---- witness generation, first slice: the SimpleGenerators of the u32 custom gates, batched on the device ----
+ * For every row whose gate (common->gate_ids[row_gate[row]]) is U32ArithmeticGate / U32AddManyGate / U32SubtractionGate /
+ * U32RangeCheckGate / ComparisonGate / U32InterleaveGate / UninterleaveToU32Gate / UninterleaveToB32Gate, the gate's DERIVED wires
+ * (outputs, carries / borrows, inverse, 2-bit-limb and bit decompositions, chunk flags) are computed from its INPUT wires, in
+ * place in the column-major wire matrix [num_wires][n]  (crypto/plonky2_u32/src/gates/*.rs `run_once`; one thread per (row, op)).
+ * Rows of other gates are left untouched.  The dependency ordering of generators and the non-native / BigUint gadget generators
+ * stay in Rust; the patched witness loop hands the rows of one dependency level to this call.  rows_filled (optional): rows touched. */
+int b200_witness_fill_u32(b200_ctx *ctx, const b200_common *common, const uint32_t *row_gate, uint64_t *wires, uint32_t *rows_filled);
+int b200_witness_fill_u32_dev(b200_ctx *ctx, const b200_common *common, const uint32_t *row_gate, uint64_t *d_wires, uint32_t *rows_filled);
+
 /* ---- prove ----
  * wires: [num_wires][n] column-major (the full witness), public_inputs: [num_public_inputs].
  * pow_witness_hint: 0 = grind the minimum nonce (== reference with RAYON_NUM_THREADS=1); otherwise the value is
@@ -182,6 +192,28 @@ int b200_msm_g2_dev(b200_ctx *ctx, const uint64_t *d_points, const uint64_t *d_s
  * inverse = 1: a[i] = n^-1 sum_k A[k] w^(-ik)   (coset != 0: a[i] *= 5^-i afterwards).  log_n <= 28. */
 int b200_fr_ntt(b200_ctx *ctx, const uint64_t *values, uint32_t log_n, int inverse, int coset, uint64_t *out);
 int b200_fr_ntt_dev(b200_ctx *ctx, const uint64_t *d_values, uint32_t log_n, int inverse, int coset, uint64_t *d_out);
+/* groth16.Prove as a pipeline over the pieces above (gnark-plonky2-verifier/cmd/web-api.go:77 -> gnark v0.9.1
+ * backend/groth16/bn254/prove.go, not vendored): H = (A.B - C)/Z by seven F_r transforms and a pointwise pass, the A / B1 / B2 /
+ * K / Z multi-scalar multiplications, blinding by (r, s) and assembly.  The proving key lives on the device.
+ *   wires    [num_wires][4]     the full R1CS solution, public wires (incl. the constant-one wire) first
+ *   a, b, c  [2^log_domain][4]  <A_j, w>, <B_j, w>, <C_j, w> per constraint j, zero-padded to the domain (gnark's solver output)
+ *   r, s     4 u64 each         blinding scalars (gnark draws them at random)
+ *   proof    32 u64             Ar (G1, 8) | Bs (G2, 16) | Krs (G1, 8), affine canonical limbs
+ * All scalars canonical < r (BN254 group order), 4 little-endian u64; points as for b200_msm_g1 / b200_msm_g2. */
+typedef struct b200_groth16_pk b200_groth16_pk;
+typedef struct {
+    uint32_t log_domain;
+    uint64_t num_wires, num_public;       /* num_public counts the constant-one wire */
+    const uint64_t *g1_a, *g1_b;          /* [num_wires][8] */
+    const uint64_t *g2_b;                 /* [num_wires][16] */
+    const uint64_t *g1_k;                 /* [num_wires - num_public][8]: (beta A_i + alpha B_i + C_i)(tau) / delta for the private wires */
+    const uint64_t *g1_z;                 /* [2^log_domain - 1][8]: tau^k Z(tau) / delta */
+    uint64_t g1_alpha[8], g1_beta[8], g1_delta[8], g2_beta[16], g2_delta[16];
+} b200_groth16_pk_desc;
+int b200_groth16_pk_upload(b200_ctx *ctx, const b200_groth16_pk_desc *desc, b200_groth16_pk **out);
+void b200_groth16_pk_free(b200_groth16_pk *pk);
+int b200_groth16_prove(b200_ctx *ctx, const b200_groth16_pk *pk, const uint64_t *wires, const uint64_t *a, const uint64_t *b,
+                       const uint64_t *c, const uint64_t r[4], const uint64_t s[4], uint64_t proof[32]);
 /* Poseidon permutation of `count` independent 12-word states (self-test / throughput probe). */
 int b200_poseidon_permute(b200_ctx *ctx, uint64_t *states, size_t count);
 

@@ -27,18 +27,17 @@ static void ref_ntt(std::vector<u64> &a, int L, bool inv) {     // natural -> na
 template <int MODE>
 static void run_pass(const N2Pass &p, const u64 *in, u64 *out, const u64 *tw, const u64 *scale, u64 out_mul) {
     const u32 tiles = 1u << (p.L - 12);
-    std::vector<u64> IN(N2_BUF_WORDS), SC(N2_BUF_WORDS), WORK(N2_BUF_WORDS), twB(256), twC(16);
+    std::vector<u64> IN(N2_BUF_WORDS), WORK(N2_BUF_WORDS), twB(256), twC(16);
     for (u32 pos = 0; pos < tiles; pos++) {
         for (u32 r = 0; r < 256; r++) {
             u64 off = MODE == 1 ? n2_row_global_bitrev(p, pos, r) : n2_row_global(p, pos, r);
             memcpy(&IN[r * N2_ROW_WORDS], in + off, 128);
-            if (MODE == 1 && scale) memcpy(&SC[r * N2_ROW_WORDS], scale + off, 128);
         }
         for (u32 t = 0; t < 240; t++) twB[(t / 15) * 16 + t % 15] = n2_twB_entry<MODE>(p, tw, pos, t / 15, t % 15);
         for (u32 t = 0; t < 15; t++) twC[t] = n2_twC_entry(tw, t);
         std::vector<u64> A(256 * 15, 0);
         for (u32 tid = 0; tid < 256; tid++) { u64 (&a)[15] = *reinterpret_cast<u64 (*)[15]>(&A[tid * 15]); n2_build_twsA<MODE>(p, tw, pos, tid, a); }
-        for (u32 tid = 0; tid < 256; tid++) { u64 (&a)[15] = *reinterpret_cast<u64 (*)[15]>(&A[tid * 15]); n2_first_round<MODE>(p, IN.data(), MODE == 1 && scale ? SC.data() : nullptr, WORK.data(), tid, a, twB.data()); }
+        for (u32 tid = 0; tid < 256; tid++) { u64 (&a)[15] = *reinterpret_cast<u64 (*)[15]>(&A[tid * 15]); n2_first_round<MODE>(p, IN.data(), MODE == 1 && scale ? scale + n2_row_global_bitrev(p, pos, tid) : nullptr, WORK.data(), tid, a, twB.data()); }
         bool third = false;
         for (u32 tid = 0; tid < 256; tid++) third = n2_second_round<MODE>(p, WORK.data(), tid, twB.data(), twC.data(), out_mul);
         if (third) for (u32 tid = 0; tid < 256; tid++) n2_third_round(WORK.data(), tid, twC.data(), out_mul);

@@ -175,3 +175,44 @@ def test_circuit_build_on_device_equals_upload_and_is_cached(kind, db, hasher):
     assert hit == np.array_equal(d.constants_sigmas, a.constants_sigmas)
     for x in (a, b, c, d): x.free()
     ctx.close()
+
+
+@pytest.mark.parametrize("kind,db", [("sig", 10), ("sha", 9)])
+def test_u32_generators_on_device_reproduce_the_witness(kind, db):
+    """f2, first slice: b200_witness_fill_u32 recomputes every derived wire of the u32 gate rows (outputs, carries, inverses, limb /
+    bit decompositions, comparison flags) from the gates' input wires; the result must be the witness the host recipes built
+    (which satisfies every gate constraint: tests/test_gate_parity.py, and matches the reference's get_wires recipes:
+    tests/test_reference_gate_cases.py)."""
+    import re, b200_plonky2 as bp
+    from b200_plonky2 import workloads
+    ctx = bp.Context(0)
+    cd = workloads.build(kind, db, seed=13)
+    gates = cd.common["gates"]; rg = cd.build_inputs["row_gate"]
+    w = cd.wires.copy()
+    def inputs_of(gid):      # (input wire columns, wires the gate uses) per gate id: everything else below num_wires is derived
+        m = re.search(r"num_ops: (\d+)", gid); n = int(m[1]) if m else 0
+        if gid.startswith("U32ArithmeticGate"): return [6 * i + k for i in range(n) for k in range(3)], 38 * n
+        if gid.startswith("U32AddManyGate"):
+            na = int(re.search(r"num_addends: (\d+)", gid)[1]); return [(na + 3) * i + k for i in range(n) for k in range(na + 1)], (na + 21) * n
+        if gid.startswith("U32SubtractionGate"): return [5 * i + k for i in range(n) for k in range(3)], 21 * n
+        if gid.startswith("U32RangeCheckGate"): l = int(re.search(r"num_input_limbs: (\d+)", gid)[1]); return list(range(l)), 17 * l
+        if gid.startswith("U32InterleaveGate"): return [2 * i for i in range(n)], 34 * n
+        if gid.startswith("UninterleaveTo"): return [3 * i for i in range(n)], 67 * n
+        if gid.startswith("ComparisonGate"):
+            nb = int(re.search(r"num_bits: (\d+)", gid)[1]); nc = int(re.search(r"num_chunks: (\d+)", gid)[1]); return [0, 1], 4 + 5 * nc + -(-nb // nc) + 1
+        return None
+    touched = 0
+    for gi, gid in enumerate(gates):
+        io = inputs_of(gid)
+        if io is None: continue
+        ins, nw = io
+        rows = np.nonzero(rg == gi)[0]
+        if not len(rows): continue
+        keep = w[np.ix_(ins, rows)].copy()
+        w[np.ix_(list(range(nw)), rows)] = np.uint64(0x1234567)      # garbage in every wire the gate uses ...
+        w[np.ix_(ins, rows)] = keep                                  # ... except the generator inputs
+        touched += len(rows)
+    assert touched > 50
+    assert cd.fill_u32_witness(ctx, w) == touched
+    assert np.array_equal(w, cd.wires)
+    ctx.close()

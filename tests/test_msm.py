@@ -124,3 +124,31 @@ def test_msm_g2_edge_cases_and_linearity(ctx):
     ra, rb, rab = ctx.msm_g2(Pn, A), ctx.msm_g2(Pn, B), ctx.msm_g2(Pn, AB)
     assert ec.g2_add(ra, rb) == rab
     assert ra == ec.g2_mul(sum(x * ks[int(i)] for x, i in zip(a, idx)) % ec.R, ec.G2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["g1", "g2"])
+def test_msm_groth16_like_skewed_scalars(ctx, group):
+    """Groth16 witness-like scalars: most wires are 0 or 1, many are small, few are full-size.  With 2^17 points the buckets of
+    digit 1 (and of the all-equal high digits of -1) hold tens of thousands of points each: they must take the sliced
+    hot-bucket path (k_hot_partial / k_hot_reduce) and still give the exact group element (closed form via discrete logs)."""
+    n = 1 << 17
+    rng = np.random.default_rng(21)
+    if group == "g1":
+        base = [ec.mul(k, ec.G) for k in range(1, 65)]; rows = [_limbs(p[0]) + _limbs(p[1]) for p in base]
+    else:
+        base = [ec.g2_mul(k, ec.G2) for k in range(1, 65)]; rows = [_g2_row(p) for p in base]
+    idx = rng.integers(0, 64, size=n)
+    P = np.array(rows, dtype=np.uint64)[idx]
+    kind = rng.random(n)
+    scal = []
+    for i in range(n):
+        if kind[i] < 0.45: scal.append(0)
+        elif kind[i] < 0.80: scal.append(1)
+        elif kind[i] < 0.90: scal.append(int(rng.integers(0, 1 << 16)))
+        elif kind[i] < 0.95: scal.append(ec.R - 1)                      # -1: every window digit equal (0xFFFF..., hot in all windows)
+        else: scal.append(int.from_bytes(rng.bytes(32), "little") % ec.R)
+    S = np.array([_limbs(s) for s in scal], dtype=np.uint64)
+    dl = sum(s * (int(i) + 1) for s, i in zip(scal, idx)) % ec.R
+    if group == "g1": assert ctx.msm_g1(P, S) == ec.mul(dl, ec.G)
+    else: assert ctx.msm_g2(P, S) == ec.g2_mul(dl, ec.G2)

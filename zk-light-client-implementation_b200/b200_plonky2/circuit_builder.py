@@ -322,6 +322,16 @@ class CircuitData:
         self._handle = h; self._ctx = ctx
         return bool(hit.value)
 
+    def fill_u32_witness(self, ctx, wires):
+        """run the u32 gates' generators on the device over `wires` ([num_wires][n], in place); returns the number of rows filled"""
+        from . import lib, c_void_p
+        cc = self.c_common()
+        w = np.ascontiguousarray(wires, dtype=np.uint64)
+        cnt = ctypes.c_uint32(0)
+        ctx._chk(lib.b200_witness_fill_u32(ctx.h, ctypes.byref(cc), self.build_inputs["row_gate"].ctypes.data_as(c_void_p), w.ctypes.data_as(c_void_p), ctypes.byref(cnt)))
+        if w is not wires: wires[...] = w
+        return int(cnt.value)
+
     def prove(self, ctx, wires=None, public_inputs=None, pow_witness_hint=0):
         """CircuitData::prove(pw): returns ProofWithPublicInputs::to_bytes()."""
         from . import lib, c_void_p, c_size_t
@@ -483,7 +493,7 @@ def fill_comparison(b, rng, cnt, bits=32, chunks=16):
     for i in range(chunks):
         f = (first >> np.uint64(cb * i)) & mask; s = (second >> np.uint64(cb * i)) & mask
         diff = F.sub(s, f); eq = (f == s)
-        dummy = np.where(eq, np.uint64(0), F.inv(np.where(eq, np.uint64(1), diff)))
+        dummy = np.where(eq, np.uint64(1), F.inv(np.where(eq, np.uint64(1), diff)))      # ONE when equal, as ComparisonGenerator (comparison.rs:472-476)
         inter = np.where(eq, msd, np.uint64(0))
         w[:, 4 + i] = f; w[:, 4 + chunks + i] = s; w[:, 4 + 2 * chunks + i] = dummy
         w[:, 4 + 3 * chunks + i] = eq.astype(np.uint64); w[:, 4 + 4 * chunks + i] = inter

@@ -69,14 +69,23 @@ _sig("b200_fr_ntt_dev", c_int, c_void_p, c_void_p, c_u32, c_int, c_int, c_void_p
 _sig("b200_circuit_build", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("b200_circuit_digest", c_int, c_u32, c_void_p, c_u32, c_u32, c_void_p)
 _sig("b200_ctx_cache_stats", c_int, c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("b200_witness_fill_u32", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+_sig("b200_witness_fill_u32_dev", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
+class Groth16PkDesc(ctypes.Structure):
+    _fields_ = [("log_domain", c_u32), ("num_wires", c_u64), ("num_public", c_u64), ("g1_a", c_void_p), ("g1_b", c_void_p), ("g2_b", c_void_p),
+                ("g1_k", c_void_p), ("g1_z", c_void_p), ("g1_alpha", c_u64 * 8), ("g1_beta", c_u64 * 8), ("g1_delta", c_u64 * 8),
+                ("g2_beta", c_u64 * 16), ("g2_delta", c_u64 * 16)]
+_sig("b200_groth16_pk_upload", c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p))
+_sig("b200_groth16_pk_free", None, c_void_p)
+_sig("b200_groth16_prove", c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p)
 _sig("b200_verify", c_int, c_void_p, c_void_p, c_void_p, c_size_t)
 _sig("b200_verify_error", ctypes.c_char_p)
 
 EXPORTS = ["b200_ctx_create", "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_synchronize", "b200_last_error",
-           "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_build", "b200_circuit_digest", "b200_ctx_cache_stats", "b200_circuit_free", "b200_prove",
+           "b200_free", "b200_host_alloc", "b200_host_free", "b200_kernel_launches", "b200_ctx_enable_timing", "b200_ctx_timings", "b200_circuit_upload", "b200_circuit_build", "b200_circuit_digest", "b200_ctx_cache_stats", "b200_circuit_free", "b200_witness_fill_u32", "b200_witness_fill_u32_dev", "b200_prove",
            "b200_prove_dev", "b200_ntt_batch", "b200_ntt_batch_dev", "b200_lde_commit", "b200_lde_commit_dev",
            "b200_poseidon_merkle", "b200_poseidon_merkle_dev", "b200_merkle_num_u64", "b200_fri_fold",
-           "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev", "b200_msm_g2", "b200_msm_g2_dev", "b200_fr_ntt", "b200_fr_ntt_dev"]
+           "b200_poseidon_permute", "b200_verify", "b200_verify_error", "b200_msm_g1", "b200_msm_g1_dev", "b200_msm_g2", "b200_msm_g2_dev", "b200_fr_ntt", "b200_fr_ntt_dev", "b200_groth16_pk_upload", "b200_groth16_pk_free", "b200_groth16_prove"]
 
 def _np(a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
@@ -166,6 +175,25 @@ class Context:
         self._chk(lib.b200_msm_g2(self.h, pp, sp, p.shape[0], out.ctypes.data_as(c_void_p)))
         v = [sum(int(out[4 * k + i]) << (64 * i) for i in range(4)) for k in range(4)]
         return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
+    def groth16_pk_upload(self, log_domain, num_public, g1_a, g1_b, g2_b, g1_k, g1_z, g1_alpha, g1_beta, g1_delta, g2_beta, g2_delta):
+        """arrays of affine points as u64 limb rows ([n][8] for G1, [n][16] for G2); returns an opaque handle (free with groth16_pk_free)"""
+        arrs = [np.ascontiguousarray(x, dtype=np.uint64) for x in (g1_a, g1_b, g2_b, g1_k, g1_z)]
+        d = Groth16PkDesc(); d.log_domain = log_domain; d.num_wires = arrs[0].shape[0]; d.num_public = num_public
+        d.g1_a, d.g1_b, d.g2_b, d.g1_k, d.g1_z = [a.ctypes.data_as(c_void_p) if a.size else None for a in arrs]
+        for name, v, n in (("g1_alpha", g1_alpha, 8), ("g1_beta", g1_beta, 8), ("g1_delta", g1_delta, 8), ("g2_beta", g2_beta, 16), ("g2_delta", g2_delta, 16)):
+            for i in range(n): getattr(d, name)[i] = int(v[i])
+        h = c_void_p()
+        self._chk(lib.b200_groth16_pk_upload(self.h, ctypes.byref(d), ctypes.byref(h)))
+        return h
+    def groth16_pk_free(self, h): lib.b200_groth16_pk_free(h)
+    def groth16_prove(self, pk, wires, a, b, c, r, s):
+        """wires [num_wires][4], a/b/c [domain][4] u64 limbs, r/s ints -> 32 u64 limbs: Ar (8) | Bs in G2 (16) | Krs (8)"""
+        W, pw = _np(wires); A, pa = _np(a); B, pb = _np(b); C, pc = _np(c)
+        lim = lambda x: np.array([(int(x) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+        R, S = lim(r), lim(s)
+        out = np.zeros(32, dtype=np.uint64)
+        self._chk(lib.b200_groth16_prove(self.h, pk, pw, pa, pb, pc, R.ctypes.data_as(c_void_p), S.ctypes.data_as(c_void_p), out.ctypes.data_as(c_void_p)))
+        return out
     def fr_ntt(self, values, inverse=False, coset=False):
         """values: [n][4] u64 canonical limbs of BN254 F_r elements (natural order) -> transformed [n][4]."""
         a, p = _np(values)

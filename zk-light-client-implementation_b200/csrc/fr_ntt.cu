@@ -162,6 +162,7 @@ static int fr_ntt_dev(b200_ctx *ctx, const uint64_t *d_in, uint32_t log_n, int i
     } catch (const ApiErr &e) { return ctx_fail(ctx, e.code, e.msg); }
 }
 
+int fr_ntt_dev_internal(b200_ctx *ctx, const uint64_t *d_in, uint32_t log_n, int inverse, int coset, uint64_t *d_out) { return fr_ntt_dev(ctx, d_in, log_n, inverse, coset, d_out); }
 extern "C" int b200_fr_ntt_dev(b200_ctx *ctx, const uint64_t *d_values, uint32_t log_n, int inverse, int coset, uint64_t *d_out) {
     return fr_ntt_dev(ctx, d_values, log_n, inverse, coset, d_out);
 }

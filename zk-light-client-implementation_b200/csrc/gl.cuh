@@ -23,19 +23,65 @@ typedef uint8_t u8;
 #define GL_HD inline
 #endif
 
-GL_HD u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+// Device versions are 32-bit carry chains in PTX: the compiler's translation of the C forms below goes through predicates
+// (ISETP / SEL pairs, ~11 instructions per modular add), and these kernels are bound by the integer ALU pipe
+// (profiles/ncu_ntt2_r02_v3.jsonl: alu 75 %, fma 35 %): 9 / 5 / 6 instructions for add / sub / canonicalise.
+GL_HD u64 gl_canon(u64 a) {          // any u64 -> canonical
+#ifdef __CUDA_ARCH__
+    u32 r0, r1;
+    asm("{\n\t.reg .u32 t0, t1, c;\n\t"
+        "add.cc.u32 t0, %2, 0xFFFFFFFF;\n\t"      // carry out of a + EPS  <=>  a >= p
+        "addc.cc.u32 t1, %3, 0;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 c, c;\n\t"                        // mask == EPS when a >= p
+        "add.cc.u32 %0, %2, c;\n\t"                // a + EPS == a - p (mod 2^64)
+        "addc.u32 %1, %3, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1) : "r"((u32)a), "r"((u32)(a >> 32)));
+    return ((u64)r1 << 32) | r0;
+#else
+    return a >= GL_P ? a - GL_P : a;
+#endif
+}
 
 // a, b canonical -> canonical
 GL_HD u64 gl_add(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    u32 r0, r1;
+    asm("{\n\t.reg .u32 s0, s1, t0, t1, c;\n\t"
+        "add.cc.u32 s0, %2, %4;\n\t"
+        "addc.cc.u32 s1, %3, %5;\n\t"
+        "addc.u32 c, 0, 0;\n\t"                    // a + b >= 2^64
+        "add.cc.u32 t0, s0, 0xFFFFFFFF;\n\t"       // or (a + b mod 2^64) >= p: never both
+        "addc.cc.u32 t1, s1, 0;\n\t"
+        "addc.u32 c, c, 0;\n\t"
+        "neg.s32 c, c;\n\t"
+        "add.cc.u32 %0, s0, c;\n\t"                // subtract p in either case (== add EPS mod 2^64)
+        "addc.u32 %1, s1, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)r1 << 32) | r0;
+#else
     u64 s = a + b;
     if (s < a) s += GL_EPS;            // wrapped past 2^64: 2^64 == EPS (mod p); result already < p
     else if (s >= GL_P) s -= GL_P;
     return s;
+#endif
 }
 GL_HD u64 gl_sub(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    u32 r0, r1;
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"                    // borrow mask == EPS
+        "sub.cc.u32 %0, %0, m;\n\t"                // + p  ==  - EPS (mod 2^64)
+        "subc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)r1 << 32) | r0;
+#else
     u64 d = a - b;
     if (a < b) d -= GL_EPS;            // + p  ==  - EPS (mod 2^64)
     return d;
+#endif
 }
 GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 

@@ -14,9 +14,11 @@
 //     live in registers / a 2 KB shared table for hundreds of consecutive units instead of being gathered per butterfly;
 //   * a round = every thread pulls one radix-16 group (16 u64) into registers, runs 4 butterfly layers, writes back;
 //   * the unit's input rows are fetched by 256 bulk copies (one per thread) that complete on an mbarrier while the
-//     previous unit is still in its later rounds; results leave by bulk stores; two blocks per SM overlap the rest;
+//     previous unit is still in its later rounds; results leave by bulk stores from one of two work buffers, so a store
+//     drains while the next unit computes in the other buffer; two blocks per SM overlap the rest;
 //   * coset LDE (first pass): the coefficient tile arrives in bit-reversed storage order as 16-element runs that are
-//     exactly the radix-16 groups of the first round, the coset scale factors arrive the same way from the table.
+//     exactly the radix-16 groups of the first round; the coset scale factors of a run are 128 contiguous bytes of the
+//     table (same storage order) and are read with 128-bit loads by the thread that owns the run.
 #include "b200_internal.h"
 #include "ntt2_core.cuh"
 #include <algorithm>
@@ -51,7 +53,7 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, u32 by
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -59,8 +61,8 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int MODE>
 __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
     extern __shared__ __align__(128) u64 sm[];
-    u64 *IN = sm, *WORK = sm + N2_BUF_WORDS, *SC = sm + 2 * N2_BUF_WORDS;      // SC only for MODE 1
-    u64 *twB = sm + (MODE == 1 ? 3 : 2) * N2_BUF_WORDS;                        // [16][16] round-table (15 used per row)
+    u64 *IN = sm, *W0 = sm + N2_BUF_WORDS, *W1 = sm + 2 * N2_BUF_WORDS;        // input rows; two work buffers (the bulk store of unit w drains while unit w + 1 computes in the other)
+    u64 *twB = sm + 3 * N2_BUF_WORDS;                                          // [16][16] round-table (15 used per row)
     u64 *twC = twB + 256;                                                      // [16] uniform last-round table (MODE 2)
     u64 *bar = twC + 16;
     const u32 tid = threadIdx.x;
@@ -85,9 +87,8 @@ __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
     auto issue_load = [&](u64 w) {
         const u32 pos = (u32)(w / a.items), item = (u32)(w % a.items);
         const u64 off = MODE == 1 ? n2_row_global_bitrev(p, pos, tid) : n2_row_global(p, pos, tid);
-        mbar_arrive_expect_tx(bar, MODE == 1 && a.scale ? 256u : 128u);
+        mbar_arrive_expect_tx(bar, 128u);
         bulk_g2s(IN + tid * N2_ROW_WORDS, in_base(item) + off, 128, bar);
-        if (MODE == 1 && a.scale) bulk_g2s(SC + tid * N2_ROW_WORDS, a.scale + (u64)(item & ((1u << a.rate_bits) - 1)) * N + off, 128, bar);
     };
 
     // twiddles of the first round of a unit live in registers; they depend on the tile position only for the strided passes
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
     u32 parity = 0;
     for (u64 w = w0; w < w1; w++) {
         const u32 pos = (u32)(w / a.items), item = (u32)(w % a.items);
-        bulk_wait_read0();                                       // my row of the previous unit has left WORK
+        u64 *WORK = ((w - w0) & 1) ? W1 : W0;
+        bulk_wait_read1();                                       // my row of the unit before the previous one has left this work buffer
         if (MODE != 2 && pos != cur_pos) {                       // block-uniform
             cur_pos = pos;
             n2_build_twsA<MODE>(p, a.tw, pos, tid, twsA);
@@ -114,8 +116,9 @@ __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
             if (tid < 240) twB[(tid / 15) * 16 + tid % 15] = n2_twB_entry<MODE>(p, a.tw, pos, tid / 15, tid % 15);
         }
         mbar_wait(bar, parity); parity ^= 1;
-        __syncthreads();                                         // everyone's previous store has been read; twB visible
-        n2_first_round<MODE>(p, IN, MODE == 1 && a.scale ? SC : nullptr, WORK, tid, twsA, twB);     // IN (+SC) -> WORK
+        __syncthreads();                                         // everyone's older store has been read; twB visible
+        const u64 *sc_row = (MODE == 1 && a.scale) ? a.scale + (u64)(item & ((1u << a.rate_bits) - 1)) * N + n2_row_global_bitrev(p, pos, tid) : nullptr;
+        n2_first_round<MODE>(p, IN, sc_row, WORK, tid, twsA, twB);     // IN (x coset scale) -> WORK
         __syncthreads();
         if (w + 1 < w1) issue_load(w + 1);                       // IN / SC are free: fetch the next unit behind the remaining rounds
         if (n2_second_round<MODE>(p, WORK, tid, twB, twC, a.out_mul)) { __syncthreads(); n2_third_round(WORK, tid, twC, a.out_mul); }
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
     bulk_wait0();
 }
 
-static size_t n2_smem_bytes(int mode) { return ((mode == 1 ? 3 : 2) * N2_BUF_WORDS + 256 + 16 + 2) * sizeof(u64); }
+static size_t n2_smem_bytes(int) { return (3 * N2_BUF_WORDS + 256 + 16 + 2) * sizeof(u64); }
 
 bool ntt2_supported(int L, size_t in_stride, size_t out_stride, int rate_bits) {
     if (L < 16 || L > 20) return false;

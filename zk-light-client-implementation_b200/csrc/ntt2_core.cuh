@@ -113,13 +113,26 @@ GL_HD void n2_round_row(const u64 *in, u64 *outb, u32 row, const u64 *tws, u64 o
     for (int e = 0; e < 16; e++) dst[e] = x[e];
 }
 // first round of the bit-reversed (LDE) pass: thread = row r of the chunk layout (n2_row_global_bitrev): x_e = row[rev4(e)]
-// (times the coset scale, same layout), butterflies on mid bits [4, 8), results to the standard layout (mid * 16 + c)
-GL_HD void n2_round_bitrev_first(const u64 *in, const u64 *sc, u64 *outb, u32 r, const u64 *tws) {
+// (times the coset scale: sc_row = the 16 scale factors of this row, read straight from the table in global memory -- same
+// storage order as the coefficients), butterflies on mid bits [4, 8), results to the standard layout (mid * 16 + c)
+GL_HD void n2_round_bitrev_first(const u64 *in, const u64 *sc_row, u64 *outb, u32 r, const u64 *tws) {
     const u32 c = r >> 4, m_lo = n2_rev4(r & 15);
-    const u64 *src = in + r * N2_ROW_WORDS, *ssc = sc ? sc + r * N2_ROW_WORDS : nullptr;
+    const u64 *src = in + r * N2_ROW_WORDS;
     u64 raw[16], x[16];
+    if (sc_row) {
+        u64 sv[16];
+#ifdef __CUDA_ARCH__
 #pragma unroll
-    for (int k = 0; k < 16; k++) raw[k] = ssc ? gl_mul(src[k], ssc[k]) : src[k];
+        for (int k = 0; k < 8; k++) { const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(sc_row) + k); sv[2 * k] = t.x; sv[2 * k + 1] = t.y; }
+#else
+        for (int k = 0; k < 16; k++) sv[k] = sc_row[k];
+#endif
+#pragma unroll
+        for (int k = 0; k < 16; k++) raw[k] = gl_mul(src[k], sv[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) raw[k] = src[k];
+    }
 #pragma unroll
     for (int e = 0; e < 16; e++) x[e] = raw[((e & 1) << 3) | ((e & 2) << 1) | ((e & 4) >> 1) | ((e & 8) >> 3)];
     n2_radix<4>(x, tws);
@@ -159,8 +172,8 @@ GL_HD u64 n2_twC_entry(const u64 *tw, u32 e) {                    // uniform tab
     return tw[n2_tw_index(0, 0, s, 0, e + 1 - (1u << s))];
 }
 template <int MODE>
-GL_HD void n2_first_round(const N2Pass &p, const u64 *IN, const u64 *SC, u64 *WORK, u32 tid, const u64 (&twsA)[15], const u64 *twB) {
-    if (MODE == 1) { n2_round_bitrev_first(IN, SC, WORK, tid, twsA); return; }
+GL_HD void n2_first_round(const N2Pass &p, const u64 *IN, const u64 *sc_row, u64 *WORK, u32 tid, const u64 (&twsA)[15], const u64 *twB) {
+    if (MODE == 1) { n2_round_bitrev_first(IN, sc_row, WORK, tid, twsA); return; }
     if (MODE == 0) { n2_round_gather<4>(IN, WORK, tid, 8, twsA, 1); return; }
     if (p.B > 8) {
         const int RA = p.B - 8, iters = 16 >> RA;               // 4096 / 2^RA tasks over 256 threads
