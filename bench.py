@@ -140,7 +140,7 @@ def run_b200(args):
     ctx = bp.Context(local); ctx.set_stream(stream.cuda_stream)
 
     cd = workloads.build("sig", args.log_n, seed=1)
-    cd.upload(ctx)
+    t_b0 = time.perf_counter(); cache_hit0 = cd.build_on_device(ctx); build_cold_ms = (time.perf_counter() - t_b0) * 1e3     # b200_circuit_build: sigma / selector polynomials + commitment on the GPU
     W, n = cd.wires.shape
     host_wires = torch.from_numpy(cd.wires).pin_memory()
     dev_wires = host_wires.to("cuda", non_blocking=True)
@@ -361,19 +361,43 @@ def run_b200(args):
     alg_bytes = 8.0 * L * W + 32.0 * L
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else None
     perms = L * ((W + 7) // 8)
+    # instruction-issue view of the same kernel (what actually bounds it): thread-instructions per permutation from the committed ncu
+    # capture of this kernel and shape, times the permutations per launch, over the LIVE launch time, against the SM issue rate
+    # (4 warp-instructions per clock per SM at the clock seen during the run)
+    NCU_INSTR_PER_PERM = 23696          # profiles/ncu_k_leaves_colmajor_r02_v1.json: 23.30 G warp-instructions / 31 457 280 permutations
+    clk = sampler.summary().get("sm_mhz") or 1965
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    issue_peak = sms * 128.0 * clk * 1e6                     # thread-instructions per second
+    issue_ach = perms * NCU_INSTR_PER_PERM / (per_launch_ms * 1e-3) if per_launch_ms else None
+    lde = phases.get("lde", [0.0, 0]); intt = phases.get("intt", [0.0, 0])
+    lde_cols = W + 2 * (1 + cd.common["num_partial_products"]) + 2 * cd.common["quotient_degree_factor"]
+    lde_bytes = 72.0 * n * lde_cols                          # 8n read + 64n written per column, every LDE of one proof
     roofline = {"bound": "hbm", "kernel": "k_leaves_colmajor (Poseidon sponge over the 234-column wires LDE, 2^20 leaves)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": 2.0067e9 if args.log_n == 17 else None,
-                "traffic_source": "profiles/ncu_k_leaves_colmajor_r01_v3.json: dram read 1.970 GB + write 0.0365 GB per launch (ncu --set full, degree_bits 17)",
+                "traffic": 2.0040e9 if args.log_n == 17 else None,
+                "traffic_source": "profiles/ncu_k_leaves_colmajor_r02_v1.json: dram read 1.967 GB + write 0.0369 GB per launch (ncu --set full, degree_bits 17)",
                 "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": (leaf[0] / ms_dev) if ms_dev else None,
+                "instr_per_perm": NCU_INSTR_PER_PERM,
+                "issue_frac": (issue_ach / issue_peak) if issue_ach else None,
+                "issue": {"achieved_Tinstr_s": issue_ach / 1e12 if issue_ach else None, "peak_Tinstr_s": issue_peak / 1e12,
+                          "peak_source": f"{sms} SMs x 4 warp-instructions/clk x 32 lanes x {clk} MHz (clock sampled during the timed region)",
+                          "instr_source": "profiles/ncu_k_leaves_colmajor_r02_v1.json (smsp__inst_executed.sum, same kernel and shape); round 1: 33 200"},
                 "alu_note": {"permutations_per_launch": perms, "Mperm_per_s": perms / (per_launch_ms * 1e-3) / 1e6 if per_launch_ms else None,
-                             "ncu": {"source": "profiles/ncu_k_leaves_colmajor_r01_v5.json (ncu --set full, same kernel and shape)",
-                                     "issue_slots_active_pct": 75.3, "pipe_fmaheavy_active_pct": 84.3, "pipe_alu_active_pct": 67.0,
-                                     "instructions_per_permutation": 33200, "dram_throughput_pct_of_peak": 0.65,
-                                     "top_stalls": {"math_pipe_throttle": 0.36, "not_selected": 0.33}},
-                             "comment": "integer-ALU bound (IMAD.WIDE.U32 issue rate), not HBM bound; see DESIGN.md"}}
+                             "ncu": {"source": "profiles/ncu_k_leaves_colmajor_r02_v1.json (ncu --set full, same kernel and shape)",
+                                     "issue_slots_active_pct": 74.0, "pipe_fmaheavy_active_pct": 82.2, "pipe_alu_active_pct": 68.8,
+                                     "instructions_per_permutation": NCU_INSTR_PER_PERM, "dram_throughput_pct_of_peak": 0.89,
+                                     "top_stalls": {"math_pipe_throttle": 0.33, "not_selected": 0.32}},
+                             "comment": "bound by integer instruction issue / the FMA-heavy pipe (IMAD.WIDE.U32), not by HBM; see DESIGN.md section 3"},
+                "other_kernels": {
+                    "ntt_lde": {"kernel": "k_ntt2_pass<1> + k_ntt2_pass<2> (x8 coset LDE of all four polynomial batches of a proof, bulk-copy staged)",
+                                "achieved": lde_bytes / (lde[0] / args.steps * 1e-3) / 1e9 if lde[0] else None, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": lde_bytes / (lde[0] / args.steps * 1e-3) / 1e9 / hbm_peak if lde[0] else None,
+                                "algorithmic_bytes_per_step": lde_bytes, "ms_per_step": lde[0] / args.steps if lde[0] else None, "columns": lde_cols},
+                    "ntt_intt": {"kernel": "k_ntt2_pass<0> + k_ntt2_pass<2> (inverse NTT of the wire and Z / partial-product columns)",
+                                 "achieved": 16.0 * n * (W + 2 * (1 + cd.common["num_partial_products"])) / (intt[0] / args.steps * 1e-3) / 1e9 if intt[0] else None,
+                                 "peak": hbm_peak, "unit": "GB/s", "ms_per_step": intt[0] / args.steps if intt[0] else None}}}
     out_json = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                 "data": "synthetic", "config": workload_desc(args.log_n),
@@ -384,6 +408,25 @@ def run_b200(args):
                 "proof_bytes": proof_len[0]}
     if block is not None: out_json["bft_finality_block"] = block
     if conc is not None: out_json["concurrent_streams"] = conc
+    if world == 1:
+        # CircuitBuilder::build()'s device half (b200_circuit_build): cold = sigma / selector polynomial generation + iNTT + LDE + Merkle of
+        # the 86 constant / sigma columns + digest; cached = hashing the build inputs and finding the resident circuit (what every
+        # repeated recursive_proof / per-signature build of the reference becomes: recursion.rs:36-96, ed25519.rs:66-77)
+        try:
+            import copy as _copy
+            again = _copy.copy(cd); again._handle = None
+            t_ = time.perf_counter(); hit = again.build_on_device(ctx); cached_ms = (time.perf_counter() - t_) * 1e3
+            rec_b = workloads.build("rec", 13, seed=3)
+            t_ = time.perf_counter(); rec_b.build_on_device(ctx); rec_cold = (time.perf_counter() - t_) * 1e3
+            rec_b2 = workloads.build("rec", 13, seed=3)
+            t_ = time.perf_counter(); hit2 = rec_b2.build_on_device(ctx); rec_cached = (time.perf_counter() - t_) * 1e3
+            out_json["circuit_build"] = {"sig_2^%d_cold_ms" % args.log_n: round(build_cold_ms, 2), "sig_cached_ms": round(cached_ms, 2), "sig_cache_hit": bool(hit),
+                                         "recursive_2^13_cold_ms": round(rec_cold, 2), "recursive_2^13_cached_ms": round(rec_cached, 2), "recursive_cache_hit": bool(hit2),
+                                         "cache": ctx.cache_stats(),
+                                         "note": "host wall clock of b200_circuit_build incl. H2D of the gate placement / copy-class successor map; outside the timed proving loops"}
+            again.free(); rec_b.free(); rec_b2.free()
+        except Exception as e:
+            out_json["circuit_build"] = {"error": str(e)}
     if world == 1 and not args.no_aux:
         # the other proof shapes of one BFT-finality block (second half of BASELINE.json's metric): a recursive_proof-shaped
         # circuit (13 standard gates, 135 wires, 2^13 rows) and the final PoseidonBN128 wrap (2^12 rows), ms per proof
