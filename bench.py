@@ -213,7 +213,10 @@ def run_b200(args):
         return ms
 
     for _ in range(args.warmup): prove(True)
-    sharding.gather_proofs({rank: prove(True, full=True)}, dist, "cuda", 1, proof_len[0])   # warm torch's own CUDA kernels / NCCL
+    # warm torch's own CUDA kernels and the collective AT THE SHAPE OF THE TIMED REGION (NCCL sets up its buffers per message
+    # size on first use: ~40 ms once, which a first timed region would otherwise carry)
+    _w = prove(True, full=True)
+    sharding.gather_proofs({s_ * world + rank: _w for s_ in range(args.steps)}, dist, "cuda", args.steps, proof_len[0])
     torch.cuda.synchronize()
     sampler = ClockSampler(local); sampler.start()
     ctx.enable_timing(True); ctx.timings()

@@ -22,6 +22,7 @@
 #include "b200_internal.h"
 #include "ntt2_core.cuh"
 #include <algorithm>
+#include <atomic>
 #include <string.h>
 
 struct N2Args {
@@ -142,15 +143,20 @@ bool ntt2_supported(int L, size_t in_stride, size_t out_stride, int rate_bits) {
 // Same contract as ntt_dif (b200_internal.h) for 16 <= L <= 20.
 void ntt2_dif(const NttTables &T, const u64 *in, size_t in_stride, bool in_bitrev, u64 *out, size_t out_stride,
               int L, size_t items, int rate_bits, const u64 *scale, bool inverse, u64 out_mul, cudaStream_t st) {
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    // per-device one-time set-up (several contexts / host threads may get here concurrently: the calls are idempotent)
+    static std::atomic<unsigned long long> dev_ready{0};
+    static int sms_of[64];
+    int dev = 0; CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) throw CudaErr{cudaErrorInvalidDevice, __FILE__, __LINE__};
+    if (!((dev_ready.load() >> dev) & 1)) {
+        int n_sm = 0; CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        sms_of[dev] = n_sm > 0 ? n_sm : 148;
         CUDA_TRY(cudaFuncSetAttribute(k_ntt2_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n2_smem_bytes(0)));
         CUDA_TRY(cudaFuncSetAttribute(k_ntt2_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n2_smem_bytes(1)));
         CUDA_TRY(cudaFuncSetAttribute(k_ntt2_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n2_smem_bytes(2)));
-        attr_set = true;
+        dev_ready.fetch_or(1ULL << dev);
     }
+    const int sms = sms_of[dev];
     const u64 *tw = inverse ? T.inv : T.fwd;
     // pass 1: layers [0, 8) on strided tiles
     N2Args a; memset(&a, 0, sizeof a);

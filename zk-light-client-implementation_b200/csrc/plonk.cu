@@ -272,27 +272,54 @@ void launch_ext_pow_table(gl2 *d_table, int L, const gl2 *h_pows2, cudaStream_t 
     k_ext_pow_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_table, L, p);
     LAUNCHED(1);
 }
-__global__ void __launch_bounds__(256) k_eval_polys(const u64 *__restrict__ coeffs, int L, const gl2 *__restrict__ table, gl2 *__restrict__ out) {
+// out[p] = sum_q coeffs[p][q] * table[q].  The table (powers of the opening point) is the same for every polynomial: a block takes
+// EP_POLYS polynomials and one of EP_SEGS segments of the index range, so that a table entry is loaded once per EP_POLYS
+// products and the grid has polys/EP_POLYS x EP_SEGS blocks (one block per polynomial left two thirds of the SMs idle at 355
+// polynomials); a second tiny kernel adds the EP_SEGS partial sums.
+#define EP_POLYS 4
+#define EP_SEGS 16
+__global__ void __launch_bounds__(256) k_eval_polys(const u64 *__restrict__ coeffs, u32 num_polys, int L, const gl2 *__restrict__ table, gl2 *__restrict__ partial) {
     __shared__ u64 sa[256], sb[256];
     const size_t n = size_t(1) << L;
-    const u64 *c = coeffs + (size_t)blockIdx.x * n;
-    acc192 A = {0, 0, 0}, B = {0, 0, 0};
-    for (size_t q = threadIdx.x; q < n; q += 256) {
-        u64 v = c[q]; gl2 t = table[q];
-        acc192_mad(A, v, t.a); acc192_mad(B, v, t.b);
+    const u32 p0 = blockIdx.x * EP_POLYS, seg = blockIdx.y;
+    const size_t seg_len = (n + EP_SEGS - 1) / EP_SEGS, q0 = seg * seg_len, q1 = q0 + seg_len < n ? q0 + seg_len : n;
+    acc192 A[EP_POLYS], B[EP_POLYS];
+#pragma unroll
+    for (int k = 0; k < EP_POLYS; k++) { A[k].lo = A[k].hi = 0; A[k].top = 0; B[k].lo = B[k].hi = 0; B[k].top = 0; }
+    for (size_t q = q0 + threadIdx.x; q < q1; q += 256) {
+        const gl2 t = table[q];
+        u64 v[EP_POLYS];
+#pragma unroll
+        for (int k = 0; k < EP_POLYS; k++) v[k] = (p0 + k < num_polys) ? coeffs[(size_t)(p0 + k) * n + q] : 0;
+#pragma unroll
+        for (int k = 0; k < EP_POLYS; k++) { acc192_mad(A[k], v[k], t.a); acc192_mad(B[k], v[k], t.b); }
     }
-    sa[threadIdx.x] = acc192_reduce(A); sb[threadIdx.x] = acc192_reduce(B);
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off) { sa[threadIdx.x] = gl_add(sa[threadIdx.x], sa[threadIdx.x + off]); sb[threadIdx.x] = gl_add(sb[threadIdx.x], sb[threadIdx.x + off]); }
+#pragma unroll
+    for (int k = 0; k < EP_POLYS; k++) {
+        sa[threadIdx.x] = acc192_reduce(A[k]); sb[threadIdx.x] = acc192_reduce(B[k]);
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            if (threadIdx.x < off) { sa[threadIdx.x] = gl_add(sa[threadIdx.x], sa[threadIdx.x + off]); sb[threadIdx.x] = gl_add(sb[threadIdx.x], sb[threadIdx.x + off]); }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0 && p0 + k < num_polys) partial[(size_t)(p0 + k) * EP_SEGS + seg] = gl2_make(sa[0], sb[0]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[blockIdx.x] = gl2_make(sa[0], sb[0]);
 }
-void launch_eval_polys(const u64 *d_coeffs_br, size_t num_polys, int L, const gl2 *d_table, gl2 *d_out, cudaStream_t st) {
-    k_eval_polys<<<(unsigned)num_polys, 256, 0, st>>>(d_coeffs_br, L, d_table, d_out);
+__global__ void k_eval_polys_sum(const gl2 *__restrict__ partial, u32 num_polys, gl2 *__restrict__ out) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= num_polys) return;
+    gl2 s = gl2_make(0, 0);
+    for (int k = 0; k < EP_SEGS; k++) s = gl2_add(s, partial[(size_t)p * EP_SEGS + k]);
+    out[p] = s;
+}
+void launch_eval_polys(const u64 *d_coeffs_br, size_t num_polys, int L, const gl2 *d_table, gl2 *d_out, gl2 *d_partial, cudaStream_t st) {
+    k_eval_polys<<<dim3((unsigned)((num_polys + EP_POLYS - 1) / EP_POLYS), EP_SEGS), 256, 0, st>>>(d_coeffs_br, (u32)num_polys, L, d_table, d_partial);
+    LAUNCHED(1);
+    k_eval_polys_sum<<<(unsigned)((num_polys + 127) / 128), 128, 0, st>>>(d_partial, (u32)num_polys, d_out);
     LAUNCHED(1);
 }
+size_t eval_polys_scratch_gl2(size_t num_polys) { return num_polys * EP_SEGS; }
 
 // =====================================================================================================
 // 4. FRI: batching of all oracles into one extension-field codeword, folding, proof of work
@@ -308,6 +335,7 @@ __global__ void __launch_bounds__(128) k_fri_combine(FriCombineArgs a) {
     u32 p = 0;
     for (int o = 0; o < 4; o++) {
         const u64 *base = a.lde[o] + pos;
+#pragma unroll 8
         for (u32 c = 0; c < a.cols[o]; c++, p++) {
             u64 v = __ldg(base + (size_t)c * N);
             gl2 ap = a.apow[p];

@@ -33,8 +33,9 @@ void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, cudaStream_
 void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 num_challenges, cudaStream_t st);
 // table[q] = base^{bitrev(q)} (ext), q < 2^L ; pows2[b] = base^(2^b)
 void launch_ext_pow_table(gl2 *d_table, int L, const gl2 *h_pows2, cudaStream_t st);
-// out[p] = sum_q coeffs[p*n + q] * table[q]
-void launch_eval_polys(const u64 *d_coeffs_br, size_t num_polys, int L, const gl2 *d_table, gl2 *d_out, cudaStream_t st);
+// out[p] = sum_q coeffs[p*n + q] * table[q]; d_partial: eval_polys_scratch_gl2(num_polys) elements of scratch
+void launch_eval_polys(const u64 *d_coeffs_br, size_t num_polys, int L, const gl2 *d_table, gl2 *d_out, gl2 *d_partial, cudaStream_t st);
+size_t eval_polys_scratch_gl2(size_t num_polys);
 struct FriCombineArgs {
     const u64 *lde[4]; u32 cols[4];              // the four oracles
     const gl2 *apow;                             // alpha^p for p < total_polys (device)

@@ -125,7 +125,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     need += (wires_on_device ? 0 : rnd((size_t)W * n)) + rnd((size_t)W * n) + rnd((size_t)W * N) + rnd(dig_u64);      // wires
     need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd(pp_scratch_u64) + rnd(8);   // zs
     need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64);                        // quotient
-    need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)); // openings tables
+    need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)) + rnd(2 * eval_polys_scratch_gl2(std::max<size_t>(std::max<size_t>(W, NC + R), std::max<size_t>(nzp, nq)))); // openings tables
     need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
     Arena A; A.base = ctx_arena(ctx, need + (1 << 20)); A.cap = need + (1 << 20);
     Staging S(ctx);
@@ -234,6 +234,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     const size_t total_polys = (size_t)NC + R + W + nzp + nq;
     gl2 *d_tab = (gl2 *)A.take(2 * n), *d_tab2 = (gl2 *)A.take(2 * n);
     gl2 *d_open = (gl2 *)A.take(2 * (total_polys + nch));
+    gl2 *d_open_part = (gl2 *)A.take(2 * eval_polys_scratch_gl2(std::max<size_t>(std::max<size_t>(W, NC + R), std::max<size_t>(nzp, nq))));
     {
         PhaseTimer tm(ctx, "openings");
         gl2 p2[32]; gl2 t = zeta; for (int b = 0; b < nlog; b++) { p2[b] = t; t = gl2_mul(t, t); }
@@ -241,11 +242,11 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         t = gzeta; for (int b = 0; b < nlog; b++) { p2[b] = t; t = gl2_mul(t, t); }
         launch_ext_pow_table(d_tab2, nlog, p2, st);
         size_t off = 0;
-        launch_eval_polys(k->cs_coeffs.u(), NC + R, nlog, d_tab, d_open + off, st); off += NC + R;
-        launch_eval_polys(w_coeffs, W, nlog, d_tab, d_open + off, st); off += W;
-        launch_eval_polys(zs_coeffs, nzp, nlog, d_tab, d_open + off, st); off += nzp;
-        launch_eval_polys(q_coeffs, nq, nlog, d_tab, d_open + off, st); off += nq;
-        launch_eval_polys(zs_coeffs, nch, nlog, d_tab2, d_open + off, st);
+        launch_eval_polys(k->cs_coeffs.u(), NC + R, nlog, d_tab, d_open + off, d_open_part, st); off += NC + R;
+        launch_eval_polys(w_coeffs, W, nlog, d_tab, d_open + off, d_open_part, st); off += W;
+        launch_eval_polys(zs_coeffs, nzp, nlog, d_tab, d_open + off, d_open_part, st); off += nzp;
+        launch_eval_polys(q_coeffs, nq, nlog, d_tab, d_open + off, d_open_part, st); off += nq;
+        launch_eval_polys(zs_coeffs, nch, nlog, d_tab2, d_open + off, d_open_part, st);
     }
     std::vector<gl2> open(total_polys + nch);
     S.d2h(open.data(), d_open, open.size() * sizeof(gl2));
