@@ -45,7 +45,7 @@ static int run_cases(const char *path) {
         if (fscanf(f, "%d %d", &expect, &n) != 2) { printf("bad case header\n"); return 1; }
         std::vector<u64> wires(240, 0);
         for (int i = 0; i < n; i++) { unsigned long long v; if (fscanf(f, "%llu", &v) != 1) return 1; if (i < 240) wires[i] = (u64)v; }
-        if (!fgets(line, sizeof line, f)) line[0] = 0;          // rest of the line
+        fgets(line, sizeof line, f);                            // rest of the line
         GateDesc g; std::vector<u64> extra;
         if (!parse_gate(id.c_str(), g, extra)) { skipped++; continue; }      // parameterisation outside the product's range (e.g. 8-bit comparison chunks)
         if (extra.empty()) extra.push_back(0);
@@ -58,8 +58,7 @@ static int run_cases(const char *path) {
         if (!eval_gate_generic<FpT>(g, cc.data(), cw.data(), pi, extra.data(), cons)) return 1;
         bool gen_zero = true; for (auto &c : cons) if (c.v) gen_zero = false;
         Wires W{wires.data(), 1, 0}, C{consts.data(), 1, 0};
-        std::vector<sink_a3> apow3(apow.size()); for (size_t i = 0; i < apow.size(); i++) apow3[i] = sink_limbs(apow[i]);
-        ConstraintSink sink; sink.apow = apow3.data(); sink.apow_stride = 600; sink.reset();
+        ConstraintSink sink; sink.apow = apow.data(); sink.apow_stride = 600; sink.reset();
         u64 st[12];
         switch (g.kind) {
 #define GK(K) case K: run_kind<K>(g, C, W, pi, extra.data(), sink, st); break;
@@ -101,8 +100,7 @@ int main(int argc, char **argv) {
             for (int k = 0; k < 2; k++) for (size_t i = 0; i < cons.size(); i++) want[k] = gl_add(want[k], gl_mul(cons[i].v, apow[600 * k + i]));
             // device evaluator on the host: one "point" (stride irrelevant, pos 0, one column per wire)
             Wires W{wires.data(), 1, 0}, C{consts.data(), 1, 0};
-            std::vector<sink_a3> apow3(apow.size()); for (size_t i = 0; i < apow.size(); i++) apow3[i] = sink_limbs(apow[i]);
-            ConstraintSink sink; sink.apow = apow3.data(); sink.apow_stride = 600; sink.reset();
+            ConstraintSink sink; sink.apow = apow.data(); sink.apow_stride = 600; sink.reset();
             u64 st[12];
             switch (g.kind) {
 #define GK(K) case K: run_kind<K>(g, C, W, pi, extra.data(), sink, st); break;
@@ -117,16 +115,6 @@ int main(int argc, char **argv) {
             for (int k = 0; k < 2; k++) if (sink.result(k) != want[k]) { printf("MISMATCH %s trial %d challenge %d\n", id, trial, k); return 1; }
             checked++;
         }
-    }
-    {   // the sink alone, past its flush threshold (512 pending terms) and with extreme operands
-        const int NT = 1500;
-        std::vector<u64> ap(2 * NT), cs(NT);
-        for (int i = 0; i < NT; i++) { cs[i] = i % 7 == 0 ? ~0ULL : (i % 5 == 0 ? GL_P - 1 : rnd()); ap[i] = i % 3 == 0 ? GL_P - 1 : rnd(); ap[NT + i] = rnd(); }
-        std::vector<sink_a3> ap3(ap.size()); for (size_t i = 0; i < ap.size(); i++) ap3[i] = sink_limbs(ap[i]);
-        ConstraintSink sink; sink.apow = ap3.data(); sink.apow_stride = NT; sink.reset();
-        u64 want[2] = {0, 0};
-        for (int i = 0; i < NT; i++) { sink.push(cs[i]); for (int k = 0; k < 2; k++) want[k] = gl_add(want[k], gl_mul(gl_canon(cs[i]), ap[NT * k + i])); }
-        for (int k = 0; k < 2; k++) if (sink.result(k) != want[k]) { printf("SINK MISMATCH challenge %d\n", k); return 1; }
     }
     printf("device gate evaluators == generic evaluators on %d (gate, row) cases\n", checked);
 }

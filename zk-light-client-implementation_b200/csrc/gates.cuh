@@ -59,69 +59,28 @@ struct Wires {              // column-major matrix accessor at one LDE position
     }
 };
 
-// S_k += c * alpha_k^idx without a single carry: the constraint value c is split in its 32-bit halves, alpha_k^idx comes as three
-// limbs of 22 | 22 | 20 bits (sink_limbs), and each of the six half x limb products (< 2^54) is accumulated by ONE
-// IMAD.WIDE.U32 into its own 64-bit accumulator (room for 1024 terms; flushed into a 192-bit total every 512).  The round-1/2
-// form -- a 64x64 product (4 IMAD.WIDE + 6 carry instructions) added into a 192-bit accumulator (5 more) per challenge -- spent
-// 22 instructions per constraint on the ALU pipe, which is the pipe these kernels are bound by (profiles/ncu_gates_r02_v4.jsonl:
-// alu 72 %, fma-heavy 47 %); this form spends none there and 4 more on the FMA pipe.
-struct sink_a3 { u32 l0, l1, l2, pad; };
-GL_HD sink_a3 sink_limbs(u64 a) { sink_a3 r; r.l0 = (u32)a & 0x3FFFFFu; r.l1 = (u32)(a >> 22) & 0x3FFFFFu; r.l2 = (u32)(a >> 44); r.pad = 0; return r; }
-struct ConstraintSink {
-    const sink_a3 *apow;    // [MAX_CHALLENGES][apow_stride] limbs of the powers of alpha
+struct ConstraintSink {     // S_k += c * alpha_k^idx
+    const u64 *apow;        // [MAX_CHALLENGES][apow_stride] powers of alpha
     u32 apow_stride;
-    u64 acc[MAX_CHALLENGES][6];         // [k][3 h + l] = sum of c_h * alpha_l
-    acc192 tot[MAX_CHALLENGES];
-    u32 idx, pending;
+    acc192 acc[MAX_CHALLENGES];
+    u32 idx;
     GL_HD void reset() {
 #pragma unroll
-        for (int k = 0; k < MAX_CHALLENGES; k++) {
-            tot[k].lo = 0; tot[k].hi = 0; tot[k].top = 0;
-#pragma unroll
-            for (int j = 0; j < 6; j++) acc[k][j] = 0;
-        }
-        idx = 0; pending = 0;
+        for (int k = 0; k < MAX_CHALLENGES; k++) { acc[k].lo = 0; acc[k].hi = 0; acc[k].top = 0; }
+        idx = 0;
     }
-    GL_HD static void add_shifted(acc192 &T, u64 v, int sh) {    // T += v << sh, 0 <= sh < 128 - (bits of v beyond ... ) ; T < 2^192 by construction
-        u64 w0, w1, w2;
-        if (sh == 0) { w0 = v; w1 = 0; w2 = 0; }
-        else if (sh < 64) { w0 = v << sh; w1 = v >> (64 - sh); w2 = 0; }
-        else if (sh == 64) { w0 = 0; w1 = v; w2 = 0; }
-        else { w0 = 0; w1 = v << (sh - 64); w2 = v >> (128 - sh); }
-        u64 l = T.lo + w0; u64 c0 = l < w0;
-        u64 h = T.hi + w1; u64 c1 = h < w1;
-        u64 h2 = h + c0; c1 += h2 < c0;
-        T.lo = l; T.hi = h2; T.top += (u32)(w2 + c1);
-    }
-    GL_HD void flush() {
+    // c: ANY 64-bit representative of the constraint value (the product is exact, the accumulator is reduced at the end)
+    GL_HD void push(u64 c) {
 #pragma unroll
-        for (int k = 0; k < MAX_CHALLENGES; k++) {
-            add_shifted(tot[k], acc[k][0], 0); add_shifted(tot[k], acc[k][1], 22); add_shifted(tot[k], acc[k][2], 44);
-            add_shifted(tot[k], acc[k][3], 32); add_shifted(tot[k], acc[k][4], 54); add_shifted(tot[k], acc[k][5], 76);
-#pragma unroll
-            for (int j = 0; j < 6; j++) acc[k][j] = 0;
-        }
-        pending = 0;
+        for (int k = 0; k < MAX_CHALLENGES; k++) acc192_mad(acc[k], c, GATE_LD(apow + k * apow_stride + idx));
+        idx++;
     }
-    // c: ANY 64-bit representative of the constraint value (the products are exact, the total is reduced at the end)
+    // same, at an explicit constraint index (lets a gate produce its constraints in one pass over the wires in any order)
     GL_HD void push_at(u64 c, u32 at) {
-        const u32 c0 = (u32)c, c1 = (u32)(c >> 32);
 #pragma unroll
-        for (int k = 0; k < MAX_CHALLENGES; k++) {
-#ifdef __CUDA_ARCH__
-            const uint4 t = __ldg(reinterpret_cast<const uint4 *>(apow + k * apow_stride + at));
-            const u32 a0 = t.x, a1 = t.y, a2 = t.z;
-#else
-            const sink_a3 t = apow[k * apow_stride + at];
-            const u32 a0 = t.l0, a1 = t.l1, a2 = t.l2;
-#endif
-            acc[k][0] += (u64)c0 * a0; acc[k][1] += (u64)c0 * a1; acc[k][2] += (u64)c0 * a2;
-            acc[k][3] += (u64)c1 * a0; acc[k][4] += (u64)c1 * a1; acc[k][5] += (u64)c1 * a2;
-        }
-        if (++pending == 512) flush();
+        for (int k = 0; k < MAX_CHALLENGES; k++) acc192_mad(acc[k], c, GATE_LD(apow + k * apow_stride + at));
     }
-    GL_HD void push(u64 c) { push_at(c, idx); idx++; }
-    GL_HD u64 result(int k) { if (pending) flush(); return acc192_reduce(tot[k]); }
+    GL_HD u64 result(int k) const { return acc192_reduce(acc[k]); }
 };
 
 struct alg2 { u64 a, b; };   // extension-algebra element over the base field: a + b X, X^2 = 7

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) k_gate(QuotientArgs a, GateDesc g) {
     u64 sel = cs[g.selector_index], filt = 1;
     for (u32 r = g.group_start; r < g.group_end; r++) if (r != g.row) filt = gl_mul(filt, gl_sub((u64)r, sel));
     if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
-    ConstraintSink sink; sink.apow = a.apow3; sink.apow_stride = a.apow_stride;
+    ConstraintSink sink; sink.apow = a.apow; sink.apow_stride = a.apow_stride;
     sink.reset();
     eval_gate<KIND>(g, gc, w, a.pi_hash, a.extra, sink, &sm[KIND == G_POSEIDON ? threadIdx.x : 0], 128);
     if (!active) return;

@@ -9,7 +9,6 @@ struct QuotientArgs {
     u64 *acc;                                    // [num_challenges][N] scratch accumulator in storage (bit-reversed) order
     const GateDesc *gates; const u64 *extra; const u64 *k_is;
     const u64 *apow;                             // [MAX_CHALLENGES][apow_stride] alpha powers
-    const sink_a3 *apow3;                        // the same powers as 22|22|20-bit limbs (ConstraintSink)
     const u64 *tw_fwd;                           // twiddle table (for x = g * w_N^i)
     u32 apow_stride;
     u32 num_gates, num_selectors, num_constants, num_routed, num_wires, num_challenges, npp, qdf, num_gate_constraints;

@@ -124,7 +124,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     auto rnd = [](size_t u) { return (u * 8 + 255) & ~size_t(255); };
     need += (wires_on_device ? 0 : rnd((size_t)W * n)) + rnd((size_t)W * n) + rnd((size_t)W * N) + rnd(dig_u64);      // wires
     need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd(pp_scratch_u64) + rnd(8);   // zs
-    need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64) + rnd(4 * (size_t)MAX_CHALLENGES * (k->num_gate_constraints + 64));   // quotient, alpha tables
+    need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64);                        // quotient
     need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)) + rnd(2 * eval_polys_scratch_gl2(std::max<size_t>(std::max<size_t>(W, NC + R), std::max<size_t>(nzp, nq)))); // openings tables
     need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
     Arena A; A.base = ctx_arena(ctx, need + (1 << 20)); A.cap = need + (1 << 20);
@@ -197,14 +197,10 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         for (u32 c = 0; c < nch; c++) { u64 p = 1; for (u32 i = 0; i < apow_stride; i++) { apow[(size_t)c * apow_stride + i] = p; p = gl_mul(p, alphas[c]); } }
         u64 *d_apow = A.take(apow.size());
         S.h2d(d_apow, apow.data(), apow.size() * 8);
-        std::vector<sink_a3> apow3(apow.size());
-        for (size_t i = 0; i < apow.size(); i++) apow3[i] = sink_limbs(apow[i]);
-        sink_a3 *d_apow3 = (sink_a3 *)A.take(2 * apow3.size());
-        S.h2d(d_apow3, apow3.data(), apow3.size() * sizeof(sink_a3));
         u64 *q_vals = A.take((size_t)nch * N), *q_big = A.take((size_t)nch * N);
         QuotientArgs qa; memset(&qa, 0, sizeof qa);
         qa.cs_lde = k->cs_lde.u(); qa.wires_lde = w_lde; qa.zs_lde = zs_lde; qa.out = q_vals;
-        qa.gates = (const GateDesc *)k->d_gates.p; qa.extra = k->d_extra.u(); qa.k_is = k->d_kis.u(); qa.apow = d_apow; qa.apow3 = d_apow3; qa.tw_fwd = ctx->tw.fwd;
+        qa.gates = (const GateDesc *)k->d_gates.p; qa.extra = k->d_extra.u(); qa.k_is = k->d_kis.u(); qa.apow = d_apow; qa.tw_fwd = ctx->tw.fwd;
         qa.apow_stride = apow_stride; qa.num_gates = (u32)k->gates.size(); qa.num_selectors = k->num_selectors; qa.num_constants = NC;
         qa.num_routed = R; qa.num_wires = W; qa.num_challenges = nch; qa.npp = npp; qa.qdf = qdf; qa.num_gate_constraints = k->num_gate_constraints;
         qa.log_n = nlog; qa.rate_bits = rb;
