@@ -414,17 +414,15 @@ void launch_fri_fold(const gl2 *d_in, gl2 *d_out, int log_len, int arity_bits, g
 
 struct PowState { u64 s[12]; };
 __global__ void __launch_bounds__(128) k_pow(PowState base, int pos, u64 start, u64 count, int bits, unsigned long long *result) {
+    __shared__ u64 sm[12 * 128];                    // state word i of thread t at sm[128 * i + t] (conflict-free, as in merkle.cu)
     u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
-    if (t >= count) return;
     u64 cand = start + t;
-    if (cand >= GL_P) return;
-    u64 s[12];
+    const bool live = t < count && cand < GL_P;
+    u64 *st = sm + threadIdx.x;
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = base.s[i];
-#pragma unroll
-    for (int i = 0; i < 8; i++) if (i == pos) s[i] = cand;
-    poseidon_permute(s);
-    if ((s[7] >> (64 - bits)) == 0) atomicMin(result, (unsigned long long)cand);
+    for (int i = 0; i < 12; i++) st[128 * i] = (i == pos) ? cand : base.s[i];
+    poseidon_permute_smem(st, 128);
+    if (live && (st[128 * 7] >> (64 - bits)) == 0) atomicMin(result, (unsigned long long)cand);
 }
 void launch_pow(const u64 state[12], int pos, u64 start, u64 count, int bits, u64 *d_result, cudaStream_t st) {
     PowState b; for (int i = 0; i < 12; i++) b.s[i] = state[i];

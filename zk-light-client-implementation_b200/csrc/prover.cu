@@ -81,7 +81,13 @@ struct Staging {
 };
 
 static void put_u64(std::vector<uint8_t> &o, u64 x) { for (int i = 0; i < 8; i++) o.push_back((uint8_t)(x >> (8 * i))); }
-static void put_words(std::vector<uint8_t> &o, const u64 *w, size_t n) { for (size_t i = 0; i < n; i++) put_u64(o, w[i]); }
+static void put_words(std::vector<uint8_t> &o, const u64 *w, size_t n) {
+#if defined(__BYTE_ORDER__) && __BYTE_ORDER__ == __ORDER_LITTLE_ENDIAN__
+    const uint8_t *b = (const uint8_t *)w; o.insert(o.end(), b, b + 8 * n);       // the proof format is little-endian u64 words
+#else
+    for (size_t i = 0; i < n; i++) put_u64(o, w[i]);
+#endif
+}
 
 // host-side tiny NTT (final polynomial only)
 static void host_ntt(std::vector<u64> &a, int logn, bool inverse) {
@@ -251,14 +257,6 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     std::vector<gl2> open(total_polys + nch);
     S.d2h(open.data(), d_open, open.size() * sizeof(gl2));
     S.sync();
-    {   // the prover checks its own openings: a violated GATE constraint leaves every committed polynomial low-degree (the
-        // quotient is interpolated from its coset values), so FRI cannot see it -- only the identity at zeta can
-        const gl2 *o = open.data();
-        VanishingInput vi{W, R, NC, nch, qdf, npp, k->num_gate_constraints, k->num_selectors, nlog, k->k_is.data(), &k->gates, k->extra.data(), pi_hash,
-                          betas, gammas, alphas, zeta, o, o + NC, o + NC + R, o + NC + R + W, o + total_polys, o + NC + R + W + nch, o + NC + R + W + nzp};
-        if (const char *why = vanishing_identity_at_zeta(vi))
-            throw ApiErr{B200_ERR_UNSATISFIED, std::string("witness does not satisfy the circuit: ") + why + " (a gate constraint is violated)"};
-    }
     for (size_t i = 0; i < total_polys; i++) ch.observe_ext(open[i]);
     for (u32 i = 0; i < nch; i++) ch.observe_ext(open[total_polys + i]);
 
@@ -280,6 +278,20 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         fa.alpha_nch = gl2_pow(fri_alpha, nch); fa.tw_fwd = ctx->tw.fwd; fa.log_N = Llog; fa.out = fri_a;
         { PhaseTimer t(ctx, "fri_combine"); launch_fri_combine(fa, st); }
     }
+    // The prover checks its own openings: a violated GATE constraint leaves every committed polynomial low-degree (the
+    // quotient is interpolated from its coset values), so FRI cannot see it -- only the identity at zeta can.  The check is
+    // host work (every gate evaluated once over the extension field); it runs while the device is busy with the FRI
+    // combine and the first layer's tree.
+    bool self_checked = false;
+    auto self_check = [&]() {
+        if (self_checked) return;
+        self_checked = true;
+        const gl2 *o = open.data();
+        VanishingInput vi{W, R, NC, nch, qdf, npp, k->num_gate_constraints, k->num_selectors, nlog, k->k_is.data(), &k->gates, k->extra.data(), pi_hash,
+                          betas, gammas, alphas, zeta, o, o + NC, o + NC + R, o + NC + R + W, o + total_polys, o + NC + R + W + nch, o + NC + R + W + nzp};
+        if (const char *why = vanishing_identity_at_zeta(vi))
+            throw ApiErr{B200_ERR_UNSATISFIED, std::string("witness does not satisfy the circuit: ") + why + " (a gate constraint is violated)"};
+    };
     // commit phase: layers[l] = values (device, kept for the query phase), digests
     struct Layer { gl2 *vals; u64 *dig; int log_len, log_leaves; size_t dig_u64; };
     std::vector<Layer> layers;
@@ -296,6 +308,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         else { merkle_leaves_rowmajor((const u64 *)cur, size_t(2) << ab, Ly.log_leaves, Ly.dig, st); merkle_build(Ly.dig, Ly.log_leaves, chh, st); }
         std::vector<u64> cap(capw);
         S.d2h(cap.data(), Ly.dig + Ly.dig_u64 - capw, capw * 8);
+        self_check();
         S.sync();
         ch.observe_cap(cap.data(), ncap, HS);
         gl2 beta = ch.get_ext();
@@ -309,6 +322,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     size_t fin_n = size_t(1) << cur_log;
     std::vector<gl2> fin_vals(fin_n);
     S.d2h(fin_vals.data(), cur, fin_n * sizeof(gl2));
+    self_check();
     S.sync();
     std::vector<u64> fa(fin_n), fb(fin_n);
     for (size_t i = 0; i < fin_n; i++) { size_t r = bitrev32((u32)i, cur_log); fa[i] = fin_vals[r].a; fb[i] = fin_vals[r].b; }
@@ -387,7 +401,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     put_words(out, cap_w.data(), capw); put_words(out, cap_z.data(), capw); put_words(out, cap_q.data(), capw);
     {
         size_t o_sig = NC, o_w = NC + R, o_z = o_w + W, o_pp = o_z + nch, o_q = o_z + nzp;
-        auto put_ext = [&](size_t a, size_t b) { for (size_t i = a; i < b; i++) { put_u64(out, open[i].a); put_u64(out, open[i].b); } };
+        static_assert(sizeof(gl2) == 16, "gl2 is two packed u64 words");
+        auto put_ext = [&](size_t a, size_t b) { put_words(out, (const u64 *)(open.data() + a), 2 * (b - a)); };
         put_ext(0, o_sig); put_ext(o_sig, o_w); put_ext(o_w, o_z); put_ext(o_z, o_pp);
         put_ext(total_polys, total_polys + nch);          // plonk_zs_next
         put_ext(o_pp, o_q); put_ext(o_q, total_polys);
