@@ -15,16 +15,19 @@ u8 *ctx_arena(b200_ctx *ctx, size_t bytes) {
 }
 
 
-const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits) {
-    auto key = std::make_pair(log_n, rate_bits);
+static const u64 *lde_scale_cached(b200_ctx *ctx, int log_n, int rate_bits, bool unit_shift) {
+    auto key = std::make_pair(log_n, unit_shift ? rate_bits + 64 : rate_bits);
     auto it = ctx->lde_scale.find(key);
     if (it != ctx->lde_scale.end()) return it->second;
     u64 *p = nullptr;
     CUDA_TRY(cudaMalloc(&p, (size_t(8) << (log_n + rate_bits))));
-    lde_scale_table(p, log_n, rate_bits, GL_GEN, ctx->stream);
+    lde_scale_table(p, log_n, rate_bits, unit_shift ? 1 : GL_GEN, ctx->stream);
     ctx->lde_scale[key] = p;
     return p;
 }
+const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits) { return lde_scale_cached(ctx, log_n, rate_bits, false); }
+// the same table for the subgroup itself (shift 1): extends values on H_{2^log_n} to H_{2^(log_n + rate_bits)}
+const u64 *ctx_lde_scale_unit(b200_ctx *ctx, int log_n, int rate_bits) { return lde_scale_cached(ctx, log_n, rate_bits, true); }
 
 void commit_hash_only(b200_ctx *ctx, const u64 *d_lde, size_t cols, int log_n, int rate_bits, int cap_height, u64 *d_digests, int hasher) {
     if (hasher == HASHER_BN254) {

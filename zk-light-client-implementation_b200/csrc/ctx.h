@@ -17,7 +17,7 @@ struct b200_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     NttTables tw;
-    std::map<std::pair<int, int>, u64 *> lde_scale;   // (log_n, rate_bits) -> coset scaling table [2^rate_bits][n] (br storage)
+    std::map<std::pair<int, int>, u64 *> lde_scale;   // (log_n, rate_bits [+64: shift 1]) -> coset scaling table [2^rate_bits][n] (br storage)
     std::string err;
     void *arena = nullptr; size_t arena_bytes = 0;   // grow-only scratch for b200_prove
     u64 *tmp_q_big = nullptr;
@@ -48,6 +48,7 @@ struct PhaseTimer {     // RAII: records start/stop events for one named phase w
 u8 *ctx_arena(b200_ctx *ctx, size_t bytes);
 // coset scaling table for the LDE, cached per size
 const u64 *ctx_lde_scale(b200_ctx *ctx, int log_n, int rate_bits);
+const u64 *ctx_lde_scale_unit(b200_ctx *ctx, int log_n, int rate_bits);     // shift 1 instead of the coset generator
 // PolynomialBatch::from_values on device buffers: values [cols][n] -> coeffs_br [cols][n], lde [cols][n<<rate], digests
 void commit_values(b200_ctx *ctx, const u64 *d_values, size_t cols, int log_n, int rate_bits, int cap_height,
                    u64 *d_coeffs_br, u64 *d_lde, u64 *d_digests, int hasher = 0);

@@ -32,6 +32,25 @@ struct GateDesc {
 
 #define MAX_CHALLENGES 2
 
+// Degree of a gate's constraint polynomials in the wire/constant columns (upstream Gate::degree(); the u32 gates:
+// crypto/plonky2_u32/src/gates/*.rs `fn degree`).  Used by the quotient to evaluate low-degree gates on a sub-coset only.
+static inline u32 gate_degree(const GateDesc &g) {
+    switch (g.kind) {
+    case G_NOOP: return 0;
+    case G_CONSTANT: case G_PUBLIC_INPUT: case G_POSEIDON_MDS: return 1;
+    case G_ARITHMETIC: case G_ARITHMETIC_EXT: case G_MUL_EXT: return 3;
+    case G_BASE_SUM: return g.p[1];
+    case G_REDUCING: case G_REDUCING_EXT: return 2;
+    case G_RANDOM_ACCESS: return g.p[0] + 1;
+    case G_POSEIDON: return 7;
+    case G_COSET_INTERPOLATION: return g.p[1];
+    case G_U32_ARITHMETIC: case G_U32_ADD_MANY: case G_U32_SUBTRACTION: case G_U32_RANGE_CHECK: return 4;
+    case G_U32_INTERLEAVE: case G_UNINTERLEAVE_U32: case G_UNINTERLEAVE_B32: return 2;
+    case G_COMPARISON: { u32 d = 1u << ((g.p[0] + g.p[1] - 1) / g.p[1]); return d < 3 ? 3 : d; }     // eq * (inter + (1 - eq) * diff) is cubic
+    default: return 1u << 30;
+    }
+}
+
 // Everything below compiles for the device (the quotient kernels of plonk.cu) AND for the host: tests/gate_eval_emulation.cu
 // runs these evaluators on the CPU against the generic evaluators of verify_gates.h (which b200_verify uses and the
 // reference's golden proofs pin), so the arithmetic shortcuts below are checked without a GPU.

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) k_leaves_rowmajor_x12(const u64 *__restri
 }
 #define X12_MAX_NODES 4096          /* above this the quad form's throughput wins */
 
-#define QUAD_MAX_NODES (size_t(1) << 15)      /* up to 2^15 permutations (4 lanes each = 2^17 threads, under one wave of 148 x 2048) the launch is latency-bound */
+#define QUAD_MAX_NODES (size_t(148) * 16 * 32 / 4)      /* below ~19 k permutations a launch cannot fill the machine thread-per-permutation (2^15 on the quad form measured slower: profiles/phase_rec13_r02_v8.json) */
 
 void merkle_leaves_colmajor(const u64 *data, size_t cols, int log_L, u64 *digests, cudaStream_t st) {
     size_t L = size_t(1) << log_L;

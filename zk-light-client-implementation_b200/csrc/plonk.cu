@@ -171,29 +171,58 @@ __global__ void __launch_bounds__(128) k_quotient_perm(QuotientArgs a) {
 }
 
 // --- 2b. one kernel per gate kind: acc[k][pos] += alpha_k^{gate_off} * filter_g(x) * sum_i c_i alpha_k^i ---
+// sub_shift = s > 0: the gate's own constraints have degree <= 2^(rate_bits - s) in the columns, so P_k(x) = alpha_k^{gate_off} *
+// sum_i c_i(x) alpha_k^i is a polynomial of degree < N >> s and its values on the sub-coset g * H_{N >> s} determine it.  In the
+// bit-reversed storage order that sub-coset is the FIRST N >> s positions: the kernel runs there only and stores P_k
+// unfiltered in sub_out[k][pos]; launch_quotient extends P_k to the whole coset with two NTTs and k_gate_combine applies
+// the (degree ~ group size) selector filters.  Exact in F_p, so the quotient values do not change.
 template <int KIND>
-__global__ void __launch_bounds__(128) k_gate(QuotientArgs a, GateDesc g) {
+__global__ void __launch_bounds__(128) k_gate(QuotientArgs a, GateDesc g, u32 sub_shift, u64 *__restrict__ sub_out) {
     __shared__ u64 sm[KIND == G_POSEIDON ? 12 * 128 : 1];
     const int L = a.log_n + a.rate_bits;
-    const size_t N = size_t(1) << L;
+    const size_t N = size_t(1) << L, NP = N >> sub_shift;
     size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const bool active = pos < N;
-    if (!active) pos = N - 1;
+    const bool active = pos < NP;
+    if (!active) pos = NP - 1;
     Wires cs = {a.cs_lde, N, pos}, w = {a.wires_lde, N, pos};
     Wires gc = {a.cs_lde + (size_t)a.num_selectors * N, N, pos};
-    u64 sel = cs[g.selector_index], filt = 1;
-    for (u32 r = g.group_start; r < g.group_end; r++) if (r != g.row) filt = gl_mul(filt, gl_sub((u64)r, sel));
-    if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
+    u64 filt = 1;
+    if (!sub_out) {
+        const u64 sel = cs[g.selector_index];
+        for (u32 r = g.group_start; r < g.group_end; r++) if (r != g.row) filt = gl_mul(filt, gl_sub((u64)r, sel));
+        if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
+    }
     ConstraintSink sink; sink.apow = a.apow; sink.apow_stride = a.apow_stride;
     sink.reset();
     eval_gate<KIND>(g, gc, w, a.pi_hash, a.extra, sink, &sm[KIND == G_POSEIDON ? threadIdx.x : 0], 128);
     if (!active) return;
     const u32 gate_off = a.num_challenges + a.num_challenges * (a.npp + 1);
     for (u32 k = 0; k < a.num_challenges; k++) {
-        u64 v = gl_mul(gl_mul(filt, sink.result(k)), __ldg(a.apow + k * a.apow_stride + gate_off));
+        u64 v = gl_mul(sink.result(k), __ldg(a.apow + k * a.apow_stride + gate_off));
+        if (sub_out) { sub_out[(size_t)k * NP + pos] = v; continue; }
         u64 *p = a.acc + (size_t)k * N + pos;
-        *p = gl_add(*p, v);
+        *p = gl_add(*p, gl_mul(filt, v));
     }
+}
+
+// acc[k][pos] += sum over the sub-sampled gates of filter_g(pos) * ext_g[k][pos]
+#define MAX_SUB_GATES 24
+struct SubGates { u32 count; struct { u32 selector_index, group_start, group_end, row; const u64 *ext; } g[MAX_SUB_GATES]; };
+__global__ void __launch_bounds__(256) k_gate_combine(QuotientArgs a, SubGates sg) {
+    const size_t N = size_t(1) << (a.log_n + a.rate_bits);
+    const size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    acc192 tot[MAX_CHALLENGES];
+#pragma unroll
+    for (int k = 0; k < MAX_CHALLENGES; k++) { tot[k].lo = 0; tot[k].hi = 0; tot[k].top = 0; }
+    for (u32 i = 0; i < sg.count; i++) {
+        const u64 sel = __ldg(a.cs_lde + (size_t)sg.g[i].selector_index * N + pos);
+        u64 filt = 1;
+        for (u32 r = sg.g[i].group_start; r < sg.g[i].group_end; r++) if (r != sg.g[i].row) filt = gl_mul(filt, gl_sub((u64)r, sel));
+        if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
+        for (u32 k = 0; k < a.num_challenges; k++) acc192_mad(tot[k], filt, __ldg(sg.g[i].ext + (size_t)k * N + pos));
+    }
+    for (u32 k = 0; k < a.num_challenges; k++) { u64 *p = a.acc + (size_t)k * N + pos; *p = gl_add(*p, acc192_reduce(tot[k])); }
 }
 
 // --- 2c. out[k][natural i] = acc[k][pos] / Z_H(x) ---
@@ -207,21 +236,70 @@ __global__ void k_quotient_finish(QuotientArgs a) {
     for (u32 k = 0; k < a.num_challenges; k++) a.out[(size_t)k * N + i] = gl_mul(a.acc[(size_t)k * N + pos], a.zh_inv[i & rmask]);
 }
 
-template <int KIND> static void launch_gate(const QuotientArgs &a, const GateDesc &g, unsigned blocks, cudaStream_t st) {
-    k_gate<KIND><<<blocks, 128, 0, st>>>(a, g);
+template <int KIND> static void launch_gate(const QuotientArgs &a, const GateDesc &g, u32 sub_shift, u64 *sub_out, cudaStream_t st) {
+    const size_t NP = (size_t(1) << (a.log_n + a.rate_bits)) >> sub_shift;
+    k_gate<KIND><<<(unsigned)((NP + 127) / 128), 128, 0, st>>>(a, g, sub_shift, sub_out);
     LAUNCHED(1);
 }
 
-void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, cudaStream_t st) {
-    size_t N = size_t(1) << (a.log_n + a.rate_bits);
+// How far a gate's evaluation domain can shrink: the largest s with degree <= 2^(rate_bits - s), for gates heavy enough
+// (by constraint count) that half or more of their evaluation time outweighs the two extension NTTs; 0 = evaluate everywhere.
+u32 quotient_gate_sub_shift(const GateDesc &g, int log_n, int rate_bits) {
+    if (g.num_constraints < 32 || g.kind == G_POSEIDON || log_n < 6) return 0;
+    const u32 d = gate_degree(g);
+    u32 s = 0;
+    while ((int)s < rate_bits && s < 3 && (d << (s + 1)) <= (1u << rate_bits)) s++;
+    return s;
+}
+size_t quotient_sub_scratch_u64(const GateDesc *gates, u32 num_gates, int log_n, int rate_bits, u32 nch) {
+    const size_t N = size_t(1) << (log_n + rate_bits);
+    size_t tot = 0; u32 cnt = 0;
+    for (u32 i = 0; i < num_gates; i++) {
+        const u32 s = quotient_gate_sub_shift(gates[i], log_n, rate_bits);
+        if (!s || gates[i].num_constraints == 0 || cnt == MAX_SUB_GATES) continue;
+        cnt++; tot += (size_t)nch * (2 * (N >> s) + N) + 96;
+    }
+    return tot;
+}
+
+void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, const NttTables &tw, const u64 *const unit_scale[4], u64 *d_sub_scratch, cudaStream_t st) {
+    const int L = a.log_n + a.rate_bits;
+    size_t N = size_t(1) << L;
     unsigned blocks = (unsigned)((N + 127) / 128);
     k_quotient_perm<<<blocks, 128, 0, st>>>(a);
     LAUNCHED(1);
+    // sub-sampled gates of one shift s share three buffers: vals [cnt*nch][N>>s], coeffs (same), ext [cnt*nch][N]
+    struct Class { u32 cnt = 0; u64 *vals = nullptr, *coeffs = nullptr, *ext = nullptr; } cls[4];
+    u32 shift_of[256]; u32 slot_of[256];
+    u32 n_sub = 0;
+    for (u32 gi = 0; gi < a.num_gates && gi < 256; gi++) {
+        shift_of[gi] = 0;
+        if (h_gates[gi].num_constraints == 0 || !d_sub_scratch || n_sub == MAX_SUB_GATES) continue;
+        const u32 s = quotient_gate_sub_shift(h_gates[gi], a.log_n, a.rate_bits);
+        if (!s || !unit_scale[s]) continue;
+        shift_of[gi] = s; slot_of[gi] = cls[s].cnt++; n_sub++;
+    }
+    {
+        u64 *p = d_sub_scratch;
+        for (u32 s = 1; s < 4; s++) if (cls[s].cnt) {
+            const size_t rows = (size_t)cls[s].cnt * a.num_challenges;
+            cls[s].vals = p; p += rows * (N >> s) + 32; cls[s].coeffs = p; p += rows * (N >> s) + 32; cls[s].ext = p; p += rows * N + 32;
+        }
+    }
+    SubGates sg; sg.count = 0;
     for (u32 gi = 0; gi < a.num_gates; gi++) {
         const GateDesc &g = h_gates[gi];
         if (g.num_constraints == 0) continue;
+        const u32 s = gi < 256 ? shift_of[gi] : 0;
+        u64 *sub_out = nullptr;
+        if (s) {
+            sub_out = cls[s].vals + (size_t)slot_of[gi] * a.num_challenges * (N >> s);
+            auto &e = sg.g[sg.count++];
+            e.selector_index = g.selector_index; e.group_start = g.group_start; e.group_end = g.group_end; e.row = g.row;
+            e.ext = cls[s].ext + (size_t)slot_of[gi] * a.num_challenges * N;
+        }
         switch (g.kind) {
-#define GK(K) case K: launch_gate<K>(a, g, blocks, st); break;
+#define GK(K) case K: launch_gate<K>(a, g, s, sub_out, st); break;
         GK(G_CONSTANT) GK(G_PUBLIC_INPUT) GK(G_ARITHMETIC) GK(G_ARITHMETIC_EXT) GK(G_MUL_EXT) GK(G_BASE_SUM) GK(G_REDUCING)
         GK(G_REDUCING_EXT) GK(G_RANDOM_ACCESS) GK(G_POSEIDON_MDS) GK(G_POSEIDON) GK(G_COSET_INTERPOLATION) GK(G_U32_ARITHMETIC)
         GK(G_U32_ADD_MANY) GK(G_U32_SUBTRACTION) GK(G_U32_RANGE_CHECK) GK(G_U32_INTERLEAVE) GK(G_UNINTERLEAVE_U32)
@@ -229,6 +307,16 @@ void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, cudaStream_
 #undef GK
         default: throw CudaErr{cudaErrorInvalidValue, __FILE__, __LINE__};
         }
+    }
+    if (sg.count) {
+        for (u32 s = 1; s < 4; s++) if (cls[s].cnt) {
+            const int Lm = L - (int)s; const size_t M = size_t(1) << Lm, rows = (size_t)cls[s].cnt * a.num_challenges;
+            // values on H_M (storage order) -> coefficients of P(g X) -> values on H_N (= the whole coset, storage order)
+            ntt_dif(tw, cls[s].vals, M, true, cls[s].coeffs, M, Lm, rows, 0, nullptr, true, gl_inv((u64)M % GL_P), st);
+            ntt_dif(tw, cls[s].coeffs, M, true, cls[s].ext, N, Lm, rows << s, (int)s, unit_scale[s], false, 1, st);
+        }
+        k_gate_combine<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a, sg);
+        LAUNCHED(1);
     }
     k_quotient_finish<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a);
     LAUNCHED(1);

@@ -28,7 +28,11 @@ void launch_partial_products(const u64 *d_wires, const u64 *d_sigmas, const u64 
                              u32 num_challenges, const u64 *betas, const u64 *gammas, const u64 *tw_fwd,
                              u64 *d_zs_pp /*[nch*(1+npp)][n]*/, u64 *d_scratch /* partial_products_scratch_u64() words */, u64 *d_final_prod /*[nch]*/,
                              cudaStream_t st);
-void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, cudaStream_t st);
+// unit_scale[s] (s = 1..3): ctx_lde_scale_unit(log_n + rate_bits - s, s) or NULL; d_sub_scratch: quotient_sub_scratch_u64() words
+// (NULL: every gate is evaluated on the whole coset)
+void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, const NttTables &tw, const u64 *const unit_scale[4], u64 *d_sub_scratch, cudaStream_t st);
+u32 quotient_gate_sub_shift(const GateDesc &g, int log_n, int rate_bits);
+size_t quotient_sub_scratch_u64(const GateDesc *gates, u32 num_gates, int log_n, int rate_bits, u32 nch);
 // big[ci][.] (size N, br order, coefficients of the coset-shifted quotient) -> chunk polys coeffs_br[ci*qdf + m][n]
 void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 num_challenges, cudaStream_t st);
 // table[q] = base^{bitrev(q)} (ext), q < 2^L ; pows2[b] = base^(2^b)

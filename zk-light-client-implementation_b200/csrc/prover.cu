@@ -131,6 +131,8 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     need += (wires_on_device ? 0 : rnd((size_t)W * n)) + rnd((size_t)W * n) + rnd((size_t)W * N) + rnd(dig_u64);      // wires
     need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd(pp_scratch_u64) + rnd(8);   // zs
     need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64);                        // quotient
+    const size_t sub_scratch_u64 = quotient_sub_scratch_u64(k->gates.data(), (u32)k->gates.size(), nlog, rb, nch);
+    need += rnd(sub_scratch_u64);
     need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)) + rnd(2 * eval_polys_scratch_gl2(std::max<size_t>(std::max<size_t>(W, NC + R), std::max<size_t>(nzp, nq)))); // openings tables
     need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
     Arena A; A.base = ctx_arena(ctx, need + (1 << 20)); A.cap = need + (1 << 20);
@@ -218,7 +220,17 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
             qa.n_inv = gl_inv((u64)n % GL_P);
         }
         qa.acc = q_big;     // scratch until the iNTT overwrites it
-        { PhaseTimer t(ctx, "quotient"); launch_quotient(qa, k->gates.data(), st); }
+        // low-degree gates are evaluated on a sub-coset and extended (plonk.cu: k_gate / k_gate_combine)
+        const u64 *unit_scale[4] = {nullptr, nullptr, nullptr, nullptr};
+        u64 *d_sub = nullptr;
+        if (sub_scratch_u64) {
+            d_sub = A.take(sub_scratch_u64);
+            for (u32 gi = 0; gi < k->gates.size(); gi++) {
+                const u32 s = quotient_gate_sub_shift(k->gates[gi], nlog, rb);
+                if (s && !unit_scale[s]) unit_scale[s] = ctx_lde_scale_unit(ctx, Llog - (int)s, (int)s);
+            }
+        }
+        { PhaseTimer t(ctx, "quotient"); launch_quotient(qa, k->gates.data(), ctx->tw, unit_scale, d_sub, st); }
         // coefficients of Q(gX): DIF inverse NTT natural -> bit-reversed, scaled by 1/N
         { PhaseTimer t(ctx, "quotient_intt"); ntt_dif(ctx->tw, q_vals, N, false, q_big, N, Llog, nch, 0, nullptr, true, gl_inv((u64)N % GL_P), st); }
         // q_vals is free again: reuse as chunk coefficient storage?  keep separate buffers for clarity
