@@ -150,13 +150,13 @@ __global__ void __launch_bounds__(128) k_quotient_perm(QuotientArgs a) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     u64 t0 = gl_add(wv[j], a.gammas[c]);
-                    num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j0 + j), x))));
+                    num = gl_mul(num, gl_add(t0, gl_mul(__ldg(a.beta_kis + c * a.num_routed + j0 + j), x)));      // beta_c * k_j: one table per proof
                     den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], sg[j])));
                 }
             } else {
                 for (u32 j = j0; j < j0 + a.qdf && j < a.num_routed; j++) {
                     u64 t0 = gl_add(w[j], a.gammas[c]);
-                    num = gl_mul(num, gl_add(t0, gl_mul(a.betas[c], gl_mul(__ldg(a.k_is + j), x))));
+                    num = gl_mul(num, gl_add(t0, gl_mul(__ldg(a.beta_kis + c * a.num_routed + j), x)));
                     den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], cs[a.num_constants + j])));
                 }
             }
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(128) k_gate(QuotientArgs a, GateDesc g, u32 su
 
 // acc[k][pos] += sum over the sub-sampled gates of filter_g(pos) * ext_g[k][pos]
 #define MAX_SUB_GATES 24
-struct SubGates { u32 count; struct { u32 selector_index, group_start, group_end, row; const u64 *ext; } g[MAX_SUB_GATES]; };
+// ext: P_k on the whole coset [nch][N]; or (half-domain gates) lo = the evaluated even half, ext = the extended odd half, both [nch][N/2]
+struct SubGates { u32 count; struct { u32 selector_index, group_start, group_end, row; const u64 *lo, *ext; } g[MAX_SUB_GATES]; };
 __global__ void __launch_bounds__(256) k_gate_combine(QuotientArgs a, SubGates sg) {
     const size_t N = size_t(1) << (a.log_n + a.rate_bits);
     const size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -220,7 +221,10 @@ __global__ void __launch_bounds__(256) k_gate_combine(QuotientArgs a, SubGates s
         u64 filt = 1;
         for (u32 r = sg.g[i].group_start; r < sg.g[i].group_end; r++) if (r != sg.g[i].row) filt = gl_mul(filt, gl_sub((u64)r, sel));
         if (a.num_selectors > 1) filt = gl_mul(filt, gl_sub(0xFFFFFFFFULL, sel));
-        for (u32 k = 0; k < a.num_challenges; k++) acc192_mad(tot[k], filt, __ldg(sg.g[i].ext + (size_t)k * N + pos));
+        const u64 *src; size_t stride = N, off = pos;
+        if (sg.g[i].lo) { stride = N >> 1; src = pos < stride ? sg.g[i].lo : sg.g[i].ext; off = pos & (stride - 1); }
+        else src = sg.g[i].ext;
+        for (u32 k = 0; k < a.num_challenges; k++) acc192_mad(tot[k], filt, __ldg(src + (size_t)k * stride + off));
     }
     for (u32 k = 0; k < a.num_challenges; k++) { u64 *p = a.acc + (size_t)k * N + pos; *p = gl_add(*p, acc192_reduce(tot[k])); }
 }
@@ -257,7 +261,7 @@ size_t quotient_sub_scratch_u64(const GateDesc *gates, u32 num_gates, int log_n,
     for (u32 i = 0; i < num_gates; i++) {
         const u32 s = quotient_gate_sub_shift(gates[i], log_n, rate_bits);
         if (!s || gates[i].num_constraints == 0 || cnt == MAX_SUB_GATES) continue;
-        cnt++; tot += (size_t)nch * (2 * (N >> s) + N) + 96;
+        cnt++; tot += (size_t)nch * (2 * (N >> s) + (s == 1 ? N >> 1 : N)) + 96;
     }
     return tot;
 }
@@ -283,7 +287,7 @@ void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, const NttTa
         u64 *p = d_sub_scratch;
         for (u32 s = 1; s < 4; s++) if (cls[s].cnt) {
             const size_t rows = (size_t)cls[s].cnt * a.num_challenges;
-            cls[s].vals = p; p += rows * (N >> s) + 32; cls[s].coeffs = p; p += rows * (N >> s) + 32; cls[s].ext = p; p += rows * N + 32;
+            cls[s].vals = p; p += rows * (N >> s) + 32; cls[s].coeffs = p; p += rows * (N >> s) + 32; cls[s].ext = p; p += rows * (s == 1 ? N >> 1 : N) + 32;
         }
     }
     SubGates sg; sg.count = 0;
@@ -296,7 +300,8 @@ void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, const NttTa
             sub_out = cls[s].vals + (size_t)slot_of[gi] * a.num_challenges * (N >> s);
             auto &e = sg.g[sg.count++];
             e.selector_index = g.selector_index; e.group_start = g.group_start; e.group_end = g.group_end; e.row = g.row;
-            e.ext = cls[s].ext + (size_t)slot_of[gi] * a.num_challenges * N;
+            e.lo = s == 1 ? sub_out : nullptr;
+            e.ext = cls[s].ext + (size_t)slot_of[gi] * a.num_challenges * (s == 1 ? N >> 1 : N);
         }
         switch (g.kind) {
 #define GK(K) case K: launch_gate<K>(a, g, s, sub_out, st); break;
@@ -313,7 +318,9 @@ void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, const NttTa
             const int Lm = L - (int)s; const size_t M = size_t(1) << Lm, rows = (size_t)cls[s].cnt * a.num_challenges;
             // values on H_M (storage order) -> coefficients of P(g X) -> values on H_N (= the whole coset, storage order)
             ntt_dif(tw, cls[s].vals, M, true, cls[s].coeffs, M, Lm, rows, 0, nullptr, true, gl_inv((u64)M % GL_P), st);
-            ntt_dif(tw, cls[s].coeffs, M, true, cls[s].ext, N, Lm, rows << s, (int)s, unit_scale[s], false, 1, st);
+            // (half-domain gates: only the odd coset w_N * H_M is new -- one transform with block 1 of the scale table, (w_N)^m)
+            if (s == 1) ntt_dif(tw, cls[s].coeffs, M, true, cls[s].ext, M, Lm, rows, 0, unit_scale[s] + M, false, 1, st);
+            else ntt_dif(tw, cls[s].coeffs, M, true, cls[s].ext, N, Lm, rows << s, (int)s, unit_scale[s], false, 1, st);
         }
         k_gate_combine<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a, sg);
         LAUNCHED(1);

@@ -8,6 +8,7 @@ struct QuotientArgs {
     u64 *out;                                    // [num_challenges][N], written at the NATURAL point index
     u64 *acc;                                    // [num_challenges][N] scratch accumulator in storage (bit-reversed) order
     const GateDesc *gates; const u64 *extra; const u64 *k_is;
+    const u64 *beta_kis;                         // [num_challenges][num_routed]: beta_c * k_j
     const u64 *apow;                             // [MAX_CHALLENGES][apow_stride] alpha powers
     const u64 *tw_fwd;                           // twiddle table (for x = g * w_N^i)
     u32 apow_stride;

@@ -132,7 +132,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd(pp_scratch_u64) + rnd(8);   // zs
     need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64);                        // quotient
     const size_t sub_scratch_u64 = quotient_sub_scratch_u64(k->gates.data(), (u32)k->gates.size(), nlog, rb, nch);
-    need += rnd(sub_scratch_u64);
+    need += rnd(sub_scratch_u64) + rnd((size_t)nch * R + 8);
     need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)) + rnd(2 * eval_polys_scratch_gl2(std::max<size_t>(std::max<size_t>(W, NC + R), std::max<size_t>(nzp, nq)))); // openings tables
     need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
     Arena A; A.base = ctx_arena(ctx, need + (1 << 20)); A.cap = need + (1 << 20);
@@ -213,6 +213,13 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         qa.num_routed = R; qa.num_wires = W; qa.num_challenges = nch; qa.npp = npp; qa.qdf = qdf; qa.num_gate_constraints = k->num_gate_constraints;
         qa.log_n = nlog; qa.rate_bits = rb;
         for (u32 c = 0; c < nch; c++) { qa.betas[c] = betas[c]; qa.gammas[c] = gammas[c]; }
+        {
+            std::vector<u64> bk((size_t)nch * R);
+            for (u32 c = 0; c < nch; c++) for (u32 j = 0; j < R; j++) bk[(size_t)c * R + j] = gl_mul(betas[c], k->k_is[j]);
+            u64 *d_bk = A.take(bk.size() + 8);
+            S.h2d(d_bk, bk.data(), bk.size() * 8);
+            qa.beta_kis = d_bk;
+        }
         for (int i = 0; i < 4; i++) qa.pi_hash[i] = pi_hash[i];
         {
             u64 g_pow_n = gl_pow(GL_GEN, (u64)n), wr = gl_root_of_unity(rb), x = 1;
