@@ -75,9 +75,53 @@ static int run_cases(const char *path) {
     printf("reference gate cases: %d evaluated as the reference expects by the device and generic evaluators (%d outside the supported parameter range)\n", ran, skipped);
     return 0;
 }
+// gate_degree() (gates.cuh) is what lets the quotient evaluate a gate on a sub-coset: every constraint, restricted to a random
+// line through the space of wire / constant values, must be a polynomial of degree <= gate_degree in the line parameter
+// ((D+1)-th finite difference == 0), and the bound should be tight for at least one constraint (D-th difference != 0).
+static int check_degrees() {
+    const int NW = 240, NCST = 4;
+    int checked = 0;
+    for (const char *id : IDS) {
+        GateDesc g; std::vector<u64> extra;
+        if (!parse_gate(id, g, extra)) { printf("parse failed: %s\n", id); return 1; }
+        if (extra.empty()) extra.push_back(0);
+        const int D = (int)gate_degree(g);
+        if (D < 1 || D > 8) { printf("implausible degree %d for %s\n", D, id); return 1; }
+        std::vector<u64> wa(NW), wb(NW), ca(NCST), cb(NCST); u64 pi[4];
+        for (auto &x : wa) x = rnd(); for (auto &x : wb) x = rnd(); for (auto &x : ca) x = rnd(); for (auto &x : cb) x = rnd();
+        for (auto &x : pi) x = rnd();
+        std::vector<std::vector<FpT>> vals;                    // vals[t][i] = constraint i at parameter t
+        for (int t = 0; t <= D + 1; t++) {
+            std::vector<FpT> cw(NW), cc(NCST), cons;
+            for (int i = 0; i < NW; i++) cw[i] = FpT::from(gl_add(wa[i], gl_mul(wb[i], (u64)t)));
+            for (int i = 0; i < NCST; i++) cc[i] = FpT::from(gl_add(ca[i], gl_mul(cb[i], (u64)t)));
+            if (!eval_gate_generic<FpT>(g, cc.data(), cw.data(), pi, extra.data(), cons)) { printf("generic eval failed: %s\n", id); return 1; }
+            vals.push_back(cons);
+        }
+        auto diff = [&](int m, size_t i) {                      // m-th forward difference at 0
+            u64 acc = 0, binom = 1;
+            for (int j = 0; j <= m; j++) {
+                u64 term = gl_mul(binom % GL_P, vals[j][i].v);
+                acc = ((m - j) & 1) ? gl_sub(acc, term) : gl_add(acc, term);
+                binom = binom * (u64)(m - j) / (u64)(j + 1);
+            }
+            return acc;
+        };
+        bool tight = false;
+        for (size_t i = 0; i < vals[0].size(); i++) {
+            if (diff(D + 1, i) != 0) { printf("DEGREE VIOLATION: constraint %zu of %s exceeds gate_degree = %d\n", i, id, D); return 1; }
+            if (diff(D, i) != 0) tight = true;
+        }
+        if (!tight) { printf("gate_degree = %d is not tight for %s\n", D, id); return 1; }
+        checked++;
+    }
+    printf("gate_degree() bounds every constraint and is tight for %d gate parameterisations\n", checked);
+    return 0;
+}
 int main(int argc, char **argv) {
     srand(11);
     if (argc > 1) return run_cases(argv[1]);
+    if (check_degrees()) return 1;
     const int NW = 240, NCST = 4;
     int checked = 0;
     for (const char *id : IDS) {

@@ -32,6 +32,8 @@ def test_device_gate_evaluators_match_generic_on_host(tmp_path):
                            os.path.join(ROOT, "tests", "gate_eval_emulation.cu"), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "device gate evaluators == generic evaluators" in r.stdout, r.stdout + r.stderr
+    # the precondition of the quotient's sub-coset evaluation: gate_degree() bounds (tightly) every constraint's degree
+    assert "gate_degree() bounds every constraint and is tight for 24 gate parameterisations" in r.stdout, r.stdout
 
 def test_limb_table_generator_is_reproducible(tmp_path):
     """the committed poseidon_limb_tables.cuh is what the generator derives from the published round constants (its own
