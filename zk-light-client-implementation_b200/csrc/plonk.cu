@@ -331,21 +331,37 @@ void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, const NttTa
 
 // big[ci] holds (br order) the coefficients of Q(g X): coefficient k of Q = big-coeff_k * g^{-k} (1/N already applied).
 // chunk m coefficient k' (k = m n + k') lives at position 8*br_n(k') + br_3(m).
-__global__ void k_quotient_split(const u64 *__restrict__ big, u64 *__restrict__ chunks, int log_n, int rate_bits, u32 nch) {
+// g^{-k} for k < n comes from two small tables (k = hi * 2^lo_bits + lo): a 64-step exponentiation per element made this
+// copy kernel cost 0.4 ms per proof
+__global__ void k_split_pow_tables(u64 *__restrict__ t_lo, u64 *__restrict__ t_hi, int lo_bits, int hi_bits) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 ginv = gl_inv(GL_GEN);
+    if (i < (1u << lo_bits)) t_lo[i] = gl_pow(ginv, i);
+    if (i < (1u << hi_bits)) t_hi[i] = gl_pow(ginv, (u64)i << lo_bits);
+}
+struct SplitPows { u64 gm[16]; };           // g^{-m n}, m < 2^rate_bits
+__global__ void k_quotient_split(const u64 *__restrict__ big, u64 *__restrict__ chunks, int log_n, int rate_bits, u32 nch,
+                                 const u64 *__restrict__ t_lo, const u64 *__restrict__ t_hi, int lo_bits, SplitPows sp) {
     const size_t n = size_t(1) << log_n, N = n << rate_bits;
     size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (idx >= (size_t)nch * N) return;
     u32 ci = (u32)(idx / N); size_t rest = idx % N;
     u32 m = (u32)(rest >> log_n), q = (u32)(rest & (n - 1));         // output: chunk m, br position q
-    u32 kp = bitrev32(q, log_n);
-    u64 k = (u64)m * n + kp;
+    u32 kp = bitrev32(q, log_n);                                     // coefficient k = m n + kp
     u64 v = big[(size_t)ci * N + ((size_t)q << rate_bits) + bitrev32(m, rate_bits)];
-    u64 ginv = gl_inv(GL_GEN);
-    chunks[((size_t)ci * (1u << rate_bits) + m) * n + q] = gl_mul(v, gl_pow(ginv, k));
+    const u64 gk = gl_mul(sp.gm[m], gl_mul(__ldg(t_lo + (kp & ((1u << lo_bits) - 1))), __ldg(t_hi + (kp >> lo_bits))));
+    chunks[((size_t)ci * (1u << rate_bits) + m) * n + q] = gl_mul(v, gk);
 }
-void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 nch, cudaStream_t st) {
+size_t quotient_split_scratch_u64(int log_n) { return (size_t(1) << ((log_n + 1) / 2)) + (size_t(1) << (log_n / 2)) + 16; }
+void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 nch, u64 *d_scratch, cudaStream_t st) {
+    const int lo_bits = (log_n + 1) / 2, hi_bits = log_n - lo_bits;
+    u64 *t_lo = d_scratch, *t_hi = d_scratch + (size_t(1) << lo_bits);
+    k_split_pow_tables<<<(unsigned)(((1u << lo_bits) + 127) / 128), 128, 0, st>>>(t_lo, t_hi, lo_bits, hi_bits);
+    LAUNCHED(1);
+    SplitPows sp; const u64 gn = gl_pow(gl_inv(GL_GEN), u64(1) << log_n);
+    { u64 x = 1; for (int m = 0; m < 16; m++) { sp.gm[m] = x; x = gl_mul(x, gn); } }
     size_t total = (size_t)nch << (log_n + rate_bits);
-    k_quotient_split<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_big, d_chunks, log_n, rate_bits, nch);
+    k_quotient_split<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_big, d_chunks, log_n, rate_bits, nch, t_lo, t_hi, lo_bits, sp);
     LAUNCHED(1);
 }
 
@@ -419,6 +435,34 @@ size_t eval_polys_scratch_gl2(size_t num_polys) { return num_polys * EP_SEGS; }
 // =====================================================================================================
 // 4. FRI: batching of all oracles into one extension-field codeword, folding, proof of work
 // =====================================================================================================
+// Step 1, coefficient space: G0 = sum_p alpha^p f_p, G1 = sum_{c < nch} alpha^c Z_c as coefficient vectors (the same
+// bit-reversed coefficient order as every committed polynomial): g[0..3][q] = G0.a, G0.b, G1.a, G1.b.  The combination is
+// F-linear, so combining the n coefficients and extending the 4 resulting columns equals combining the 8n LDE values of all
+// 355 columns (what round 1 did: 3 GB of reads per proof instead of 0.37 GB).
+__global__ void __launch_bounds__(128) k_fri_coeff_combine(FriCombineArgs a) {
+    const size_t n = size_t(1) << a.log_n;
+    const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    acc192 A = {0, 0, 0}, B = {0, 0, 0};
+    u32 p = 0;
+    for (int o = 0; o < 4; o++) {
+        const u64 *base = a.coeffs[o] + q;
+#pragma unroll 8
+        for (u32 c = 0; c < a.cols[o]; c++, p++) {
+            u64 v = __ldg(base + (size_t)c * n);
+            gl2 ap = a.apow[p];
+            acc192_mad(A, v, ap.a); acc192_mad(B, v, ap.b);
+        }
+    }
+    acc192 A1 = {0, 0, 0}, B1 = {0, 0, 0};
+    for (u32 c = 0; c < a.nch; c++) {
+        u64 v = __ldg(a.coeffs[2] + (size_t)c * n + q);
+        gl2 ap = a.apow[c];
+        acc192_mad(A1, v, ap.a); acc192_mad(B1, v, ap.b);
+    }
+    a.g[q] = acc192_reduce(A); a.g[n + q] = acc192_reduce(B); a.g[2 * n + q] = acc192_reduce(A1); a.g[3 * n + q] = acc192_reduce(B1);
+}
+// Step 3, on the LDE of g: out(x) = alpha^nch * (G0(x) - y0) / (x - zeta) + (G1(x) - y1) / (x - g zeta)
 __global__ void __launch_bounds__(128) k_fri_combine(FriCombineArgs a) {
     const size_t N = size_t(1) << a.log_N;
     size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -426,29 +470,19 @@ __global__ void __launch_bounds__(128) k_fri_combine(FriCombineArgs a) {
     const u32 i = bitrev32((u32)pos, a.log_N);
     u64 x;
     { size_t h = N >> 1; u64 wi = (i < h) ? __ldg(a.tw_fwd + h + i) : gl_neg(__ldg(a.tw_fwd + h + (i - h))); x = gl_mul(GL_GEN, wi); }
-    acc192 A = {0, 0, 0}, B = {0, 0, 0};
-    u32 p = 0;
-    for (int o = 0; o < 4; o++) {
-        const u64 *base = a.lde[o] + pos;
-#pragma unroll 8
-        for (u32 c = 0; c < a.cols[o]; c++, p++) {
-            u64 v = __ldg(base + (size_t)c * N);
-            gl2 ap = a.apow[p];
-            acc192_mad(A, v, ap.a); acc192_mad(B, v, ap.b);
-        }
-    }
-    gl2 F0 = gl2_make(acc192_reduce(A), acc192_reduce(B));
-    acc192 A1 = {0, 0, 0}, B1 = {0, 0, 0};
-    for (u32 c = 0; c < a.nch; c++) {
-        u64 v = __ldg(a.lde[2] + (size_t)c * N + pos);
-        gl2 ap = a.apow[c];
-        acc192_mad(A1, v, ap.a); acc192_mad(B1, v, ap.b);
-    }
-    gl2 F1 = gl2_make(acc192_reduce(A1), acc192_reduce(B1));
-    gl2 xe = gl2_make(x, 0);
-    gl2 t0 = gl2_mul(gl2_sub(F0, a.y0), gl2_inv(gl2_sub(xe, a.zeta)));
-    gl2 t1 = gl2_mul(gl2_sub(F1, a.y1), gl2_inv(gl2_sub(xe, a.gzeta)));
+    const gl2 F0 = gl2_make(__ldg(a.g_lde + pos), __ldg(a.g_lde + N + pos));
+    const gl2 F1 = gl2_make(__ldg(a.g_lde + 2 * N + pos), __ldg(a.g_lde + 3 * N + pos));
+    const gl2 xe = gl2_make(x, 0);
+    const gl2 d0 = gl2_sub(xe, a.zeta), d1 = gl2_sub(xe, a.gzeta);
+    const gl2 mi = gl2_inv(gl2_mul(d0, d1));                    // one inversion for both denominators
+    gl2 t0 = gl2_mul(gl2_sub(F0, a.y0), gl2_mul(mi, d1));
+    gl2 t1 = gl2_mul(gl2_sub(F1, a.y1), gl2_mul(mi, d0));
     a.out[pos] = gl2_add(gl2_mul(t0, a.alpha_nch), t1);
+}
+void launch_fri_coeff_combine(const FriCombineArgs &a, cudaStream_t st) {
+    size_t n = size_t(1) << a.log_n;
+    k_fri_coeff_combine<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a);
+    LAUNCHED(1);
 }
 void launch_fri_combine(const FriCombineArgs &a, cudaStream_t st) {
     size_t N = size_t(1) << a.log_N;

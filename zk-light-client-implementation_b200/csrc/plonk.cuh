@@ -35,20 +35,24 @@ void launch_quotient(const QuotientArgs &a, const GateDesc *h_gates, const NttTa
 u32 quotient_gate_sub_shift(const GateDesc &g, int log_n, int rate_bits);
 size_t quotient_sub_scratch_u64(const GateDesc *gates, u32 num_gates, int log_n, int rate_bits, u32 nch);
 // big[ci][.] (size N, br order, coefficients of the coset-shifted quotient) -> chunk polys coeffs_br[ci*qdf + m][n]
-void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 num_challenges, cudaStream_t st);
+void launch_quotient_split(const u64 *d_big, u64 *d_chunks, int log_n, int rate_bits, u32 num_challenges, u64 *d_scratch /* quotient_split_scratch_u64(log_n) words */, cudaStream_t st);
+size_t quotient_split_scratch_u64(int log_n);
 // table[q] = base^{bitrev(q)} (ext), q < 2^L ; pows2[b] = base^(2^b)
 void launch_ext_pow_table(gl2 *d_table, int L, const gl2 *h_pows2, cudaStream_t st);
 // out[p] = sum_q coeffs[p*n + q] * table[q]; d_partial: eval_polys_scratch_gl2(num_polys) elements of scratch
 void launch_eval_polys(const u64 *d_coeffs_br, size_t num_polys, int L, const gl2 *d_table, gl2 *d_out, gl2 *d_partial, cudaStream_t st);
 size_t eval_polys_scratch_gl2(size_t num_polys);
 struct FriCombineArgs {
-    const u64 *lde[4]; u32 cols[4];              // the four oracles
+    const u64 *coeffs[4]; u32 cols[4];           // the four oracles' coefficient matrices [cols][n] (bit-reversed coefficient order)
     const gl2 *apow;                             // alpha^p for p < total_polys (device)
     u32 total_polys, nch;                        // zs oracle index is 2, its first nch columns are the Z polys
     gl2 y0, y1, zeta, gzeta, alpha_nch;          // reduced openings, points, alpha^{nch}
-    const u64 *tw_fwd; int log_N;
+    const u64 *tw_fwd; int log_n, log_N;
+    u64 *g;                                      // [4][n]: coefficients of G0.a, G0.b, G1.a, G1.b (launch_fri_coeff_combine writes)
+    const u64 *g_lde;                            // [4][N]: their LDE on the commitment coset (launch_fri_combine reads)
     gl2 *out;                                    // [N] bit-reversed order
 };
+void launch_fri_coeff_combine(const FriCombineArgs &a, cudaStream_t st);
 void launch_fri_combine(const FriCombineArgs &a, cudaStream_t st);
 // fold: in [len] ext (br order), out [len >> arity_bits]
 void launch_fri_fold(const gl2 *d_in, gl2 *d_out, int log_len, int arity_bits, gl2 beta, u64 shift, const u64 *tw_fwd, cudaStream_t st);

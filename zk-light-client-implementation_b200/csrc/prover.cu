@@ -132,9 +132,9 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     need += 2 * rnd((size_t)nzp * n) + rnd((size_t)nzp * N) + rnd(dig_u64) + rnd(pp_scratch_u64) + rnd(8);   // zs
     need += rnd((size_t)nch * N) * 2 + rnd((size_t)nq * n) + rnd((size_t)nq * N) + rnd(dig_u64);                        // quotient
     const size_t sub_scratch_u64 = quotient_sub_scratch_u64(k->gates.data(), (u32)k->gates.size(), nlog, rb, nch);
-    need += rnd(sub_scratch_u64) + rnd((size_t)nch * R + 8);
+    need += rnd(sub_scratch_u64) + rnd((size_t)nch * R + 8) + rnd(quotient_split_scratch_u64(nlog));
     need += rnd(2 * n) * 2 + rnd(2 * (size_t)(NC + R + W + nzp + nq + nch)) + rnd(2 * (size_t)(NC + R + W + nzp + nq)) + rnd(2 * eval_polys_scratch_gl2(std::max<size_t>(std::max<size_t>(W, NC + R), std::max<size_t>(nzp, nq)))); // openings tables
-    need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20);                                                            // fri
+    need += rnd(2 * N) * 2 + rnd(dig_u64) * 2 + rnd(1 << 20) + rnd(4 * n) + rnd(4 * N);                                                            // fri
     Arena A; A.base = ctx_arena(ctx, need + (1 << 20)); A.cap = need + (1 << 20);
     Staging S(ctx);
 
@@ -245,7 +245,7 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
         ctx->tmp_q_big = q_big;
     }
     u64 *q_coeffs = A.take((size_t)nq * n), *q_lde = A.take((size_t)nq * N), *q_dig = A.take(dig_u64);
-    launch_quotient_split(ctx->tmp_q_big, q_coeffs, nlog, rb, nch, st);
+    launch_quotient_split(ctx->tmp_q_big, q_coeffs, nlog, rb, nch, A.take(quotient_split_scratch_u64(nlog)), st);
     commit_coeffs(ctx, q_coeffs, nq, nlog, rb, chh, q_lde, q_dig, HS);
     S.d2h(cap_q.data(), q_dig + dig_u64 - capw, capw * 8);
     S.sync();
@@ -291,11 +291,16 @@ static int prove_impl(b200_ctx *ctx, const b200_circuit *k, const u64 *wires_in,
     gl2 *fri_a = (gl2 *)A.take(2 * N), *fri_b = (gl2 *)A.take(2 * N);
     {
         FriCombineArgs fa; memset(&fa, 0, sizeof fa);
-        fa.lde[0] = k->cs_lde.u(); fa.lde[1] = w_lde; fa.lde[2] = zs_lde; fa.lde[3] = q_lde;
+        fa.coeffs[0] = k->cs_coeffs.u(); fa.coeffs[1] = w_coeffs; fa.coeffs[2] = zs_coeffs; fa.coeffs[3] = q_coeffs;
         fa.cols[0] = NC + R; fa.cols[1] = W; fa.cols[2] = nzp; fa.cols[3] = nq;
         fa.apow = d_apow2; fa.total_polys = (u32)total_polys; fa.nch = nch; fa.y0 = y0; fa.y1 = y1; fa.zeta = zeta; fa.gzeta = gzeta;
-        fa.alpha_nch = gl2_pow(fri_alpha, nch); fa.tw_fwd = ctx->tw.fwd; fa.log_N = Llog; fa.out = fri_a;
-        { PhaseTimer t(ctx, "fri_combine"); launch_fri_combine(fa, st); }
+        fa.alpha_nch = gl2_pow(fri_alpha, nch); fa.tw_fwd = ctx->tw.fwd; fa.log_n = nlog; fa.log_N = Llog; fa.out = fri_a;
+        u64 *g = A.take(4 * n), *g_lde = A.take(4 * N);
+        fa.g = g; fa.g_lde = g_lde;
+        PhaseTimer t(ctx, "fri_combine");
+        launch_fri_coeff_combine(fa, st);
+        ntt_dif(ctx->tw, g, n, true, g_lde, N, nlog, (size_t)4 << rb, rb, ctx_lde_scale(ctx, nlog, rb), false, 1, st);
+        launch_fri_combine(fa, st);
     }
     // The prover checks its own openings: a violated GATE constraint leaves every committed polynomial low-degree (the
     // quotient is interpolated from its coset values), so FRI cannot see it -- only the identity at zeta can.  The check is
