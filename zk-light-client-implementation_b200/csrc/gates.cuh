@@ -138,16 +138,10 @@ GL_HD void acc128_add_shifted(acc128 &A, u64 x, int sh) {       // A += x << sh 
 }
 GL_HD u64 acc128_reduce(const acc128 &A) { return gl_canon(gl_reduce128_nc(A.lo, A.hi)); }
 
-GL_HD void mds_canon(u64 s[12]) {
-    poseidon_mds(s);
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
-}
-
-// PoseidonGate (poseidon_gate.go:92-181) evaluated with the compact permutation structure: the state lives in shared
-// memory, the S-box layer is a rolled loop, all 30 rounds share one MDS.  Partial rounds use the textbook form: the
-// S-box input of round r is (state[0] + RC[12r]) in both the textbook and the "fast" formulation the reference gate
-// is written in (checked in tests/test_gate_parity.py), so every constraint value is identical.
+// PoseidonGate (poseidon_gate.go:92-181) evaluated with the structure of the Merkle kernels' permutation: the state lives in
+// shared memory, the S-box layer is a rolled loop, the linear layers run on limb triples.  The S-box input of a partial
+// round is (state[0] + RC[12r]) in the textbook form, in the "fast" formulation the reference gate is written in (checked in
+// tests/test_gate_parity.py) and in the pushed-constant limb form used here, so every constraint value is identical.
 GATE_NOINLINE void eval_poseidon_gate_smem(const Wires &w, ConstraintSink &sink, u64 *st, const int stride) {
     {
         u64 swap = w[24];
@@ -161,36 +155,53 @@ GATE_NOINLINE void eval_poseidon_gate_smem(const Wires &w, ConstraintSink &sink,
 #pragma unroll
         for (int i = 8; i < 12; i++) st[i * stride] = w[i];
     }
-    for (int r = 0; r < 30; r++) {
-        const bool full = (r < 4) || (r >= 26);
-        const u64 *rc = PT(POSEIDON_RC) + 12 * r;
-        u64 s[12];
-        if (full) {
-            const int wbase = (r < 4) ? 29 + 12 * (r - 1) : 87 + 12 * (r - 26);
-            for (int i = 0; i < 12; i++) {
-                u64 x = gl_add(gl_canon(st[i * stride]), rc[i]);
-                if (r != 0) { u64 sin = w[wbase + i]; sink.push(gl_sub(x, sin)); x = sin; }
-                st[i * stride] = poseidon_sbox(x);
-            }
+    // The rounds follow poseidon_permute_limb (poseidon.cuh) step for step -- limb-resident linear layers, constants of the
+    // partial rounds pushed forward -- with the gate's hooks: every S-box input after round 0 is constrained against its
+    // wire and the WIRE goes through the S-box.  The constant pushing is an identity of the linear layers for arbitrary
+    // S-box outputs, so each constraint is the same field element as in the textbook form (host check:
+    // tests/gate_eval_emulation.cu on random rows, where no constraint vanishes).
+    i32 l0[12], l1[12], l2[12];
 #pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = st[i * stride];
-        } else {
+    for (int i = 0; i < 12; i++) pl_split(st[i * stride], l0[i], l1[i], l2[i]);
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) {
+            const pl_c4 *rc = PLT(POSEIDON_L_RC) + 12 * (4 * phase + r);
+            const bool constrained = phase == 1 || r != 0;
+            const int wbase = phase == 0 ? 29 + 12 * (r - 1) : 87 + 12 * r;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
-                u64 c = rc[i];
-                u64 x = st[i * stride] + c;
-                if (x < c) x += GL_EPS;
-                s[i] = x;
+                const pl_c4 c = rc[i];
+                u64 x = pl_recombine((u32)l0[i] + c.a, (u32)l1[i] + c.b, (u32)l2[i] + c.c);
+                if (constrained) { const u64 sin = w[wbase + i]; sink.push(gl_sub(gl_canon(x), sin)); x = sin; }
+                st[i * stride] = x;
             }
-            u64 sin = w[65 + (r - 4)];
-            sink.push(gl_sub(gl_canon(s[0]), sin));
-            s[0] = poseidon_sbox(sin);
+#pragma unroll 2
+            for (int i = 0; i < 12; i++) st[i * stride] = poseidon_sbox4(st[i * stride]);
+#pragma unroll
+            for (int i = 0; i < 12; i++) pl_split(st[i * stride], l0[i], l1[i], l2[i]);
+            pl_mds(l0, l1, l2);
         }
-        poseidon_mds(s);
+        if (phase == 0) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) st[i * stride] = s[i];
+            for (int i = 1; i < 12; i++) pl_normalise(l0[i], l1[i], l2[i]);
+#pragma unroll 1
+            for (int r = 0; r < 22; r++) {
+                const pl_c4 c = PLT(POSEIDON_L_PK)[r];
+                const u64 sin = w[65 + r];
+                sink.push(gl_sub(gl_canon(pl_recombine((u32)l0[0] + c.a, (u32)l1[0] + c.b, (u32)l2[0] + c.c)), sin));
+                pl_split(poseidon_sbox4(sin), l0[0], l1[0], l2[0]);
+                pl_mds(l0, l1, l2);
+#pragma unroll
+                for (int i = 1; i < 12; i++) pl_normalise(l0[i], l1[i], l2[i]);
+            }
+        }
     }
-    for (int i = 0; i < 12; i++) sink.push(gl_sub(gl_canon(st[i * stride]), w[12 + i]));
+    const pl_c4 fin = POSEIDON_L_FIN_INIT;
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+        sink.push(gl_sub(gl_canon(pl_recombine((u32)l0[i] + fin.a, (u32)l1[i] + fin.b, (u32)l2[i] + fin.c)), w[12 + i]));
 }
 
 GATE_NOINLINE void eval_coset_interpolation(const GateDesc &g, const Wires &w, const u64 *weights, ConstraintSink &sink) {

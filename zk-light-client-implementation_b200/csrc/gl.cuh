@@ -66,6 +66,26 @@ GL_HD u64 gl_add(u64 a, u64 b) {
     return s;
 #endif
 }
+// a: ANY 64-bit representative, b: canonical -> some representative of a + b in [0, 2^64) (6 instructions instead of 9:
+// with b < p the wrapped sum plus EPS cannot wrap a second time).  For sums that feed a multiplication.
+GL_HD u64 gl_add_nc1(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    u32 r0, r1;
+    asm("{\n\t.reg .u32 c;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 c, c;\n\t"                        // EPS when a + b >= 2^64
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t}"
+        : "=&r"(r0), "=&r"(r1) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return ((u64)r1 << 32) | r0;
+#else
+    u64 s = a + b;
+    if (s < a) s += GL_EPS;
+    return s;
+#endif
+}
 GL_HD u64 gl_sub(u64 a, u64 b) {
 #ifdef __CUDA_ARCH__
     u32 r0, r1;

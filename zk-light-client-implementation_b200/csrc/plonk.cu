@@ -149,9 +149,10 @@ __global__ void __launch_bounds__(128) k_quotient_perm(QuotientArgs a) {
                 w.load<8>(j0, wv); cs.load<8>(a.num_constants + j0, sg);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
+                    // products stay non-canonical between multiplications (any 64-bit representative is a valid factor)
                     u64 t0 = gl_add(wv[j], a.gammas[c]);
-                    num = gl_mul(num, gl_add(t0, gl_mul(__ldg(a.beta_kis + c * a.num_routed + j0 + j), x)));      // beta_c * k_j: one table per proof
-                    den = gl_mul(den, gl_add(t0, gl_mul(a.betas[c], sg[j])));
+                    num = gl_mul_nc(num, gl_add_nc1(gl_mul_nc(__ldg(a.beta_kis + c * a.num_routed + j0 + j), x), t0));      // beta_c * k_j: one table per proof
+                    den = gl_mul_nc(den, gl_add_nc1(gl_mul_nc(a.betas[c], sg[j]), t0));
                 }
             } else {
                 for (u32 j = j0; j < j0 + a.qdf && j < a.num_routed; j++) {
