@@ -27,30 +27,40 @@ static void ref_ntt(std::vector<u64> &a, int L, bool inv) {     // natural -> na
 template <int MODE>
 static void run_pass(const N2Pass &p, const u64 *in, u64 *out, const u64 *tw, const u64 *scale, u64 out_mul) {
     const u32 tiles = 1u << (p.L - 12);
-    std::vector<u64> IN(N2_BUF_WORDS), WORK(N2_BUF_WORDS), twB(256), twC(16);
+    std::vector<u64> IN(N2_BUF_WORDS), WORK(N2_BUF_WORDS), twB(256);
     for (u32 pos = 0; pos < tiles; pos++) {
         for (u32 r = 0; r < 256; r++) {
             u64 off = MODE == 1 ? n2_row_global_bitrev(p, pos, r) : n2_row_global(p, pos, r);
             memcpy(&IN[r * N2_ROW_WORDS], in + off, 128);
         }
         for (u32 t = 0; t < 240; t++) twB[(t / 15) * 16 + t % 15] = n2_twB_entry<MODE>(p, tw, pos, t / 15, t % 15);
-        for (u32 t = 0; t < 15; t++) twC[t] = n2_twC_entry(tw, t);
         std::vector<u64> A(256 * 15, 0);
         for (u32 tid = 0; tid < 256; tid++) { u64 (&a)[15] = *reinterpret_cast<u64 (*)[15]>(&A[tid * 15]); n2_build_twsA<MODE>(p, tw, pos, tid, a); }
         for (u32 tid = 0; tid < 256; tid++) { u64 (&a)[15] = *reinterpret_cast<u64 (*)[15]>(&A[tid * 15]); n2_first_round<MODE>(p, IN.data(), MODE == 1 && scale ? scale + n2_row_global_bitrev(p, pos, tid) : nullptr, WORK.data(), tid, a, twB.data()); }
         bool third = false;
-        for (u32 tid = 0; tid < 256; tid++) third = n2_second_round<MODE>(p, WORK.data(), tid, twB.data(), twC.data(), out_mul);
-        if (third) for (u32 tid = 0; tid < 256; tid++) n2_third_round(WORK.data(), tid, twC.data(), out_mul);
+        for (u32 tid = 0; tid < 256; tid++) third = n2_second_round<MODE>(p, WORK.data(), tid, twB.data(), out_mul);
+        if (third) for (u32 tid = 0; tid < 256; tid++) n2_third_round(p, WORK.data(), tid, out_mul);
         for (u32 r = 0; r < 256; r++) memcpy(out + n2_row_global(p, pos, r), &WORK[r * N2_ROW_WORDS], 128);
     }
 }
+template <int T> static int check_pow2() {
+    const u64 c = gl_pow(2, T);
+    const u64 edge[] = {0, 1, GL_P - 1, GL_P - 2, 0xFFFFFFFFULL, 0x100000000ULL, 0xFFFFFFFF00000000ULL, 0xFFFFFFFEFFFFFFFFULL, 0x8000000000000000ULL};
+    for (u64 x : edge) if (gl_mul_pow2<T>(x) != gl_mul(x, c)) { printf("gl_mul_pow2<%d> mismatch on %llx\n", T, (unsigned long long)x); return 1; }
+    for (int i = 0; i < 200000; i++) { u64 x = rnd(); if (gl_mul_pow2<T>(x) != gl_mul(x, c)) { printf("gl_mul_pow2<%d> mismatch on %llx\n", T, (unsigned long long)x); return 1; } }
+    return 0;
+}
 int main() {
     srand(5);
+    if (check_pow2<12>() || check_pow2<24>() || check_pow2<36>() || check_pow2<48>() || check_pow2<60>() || check_pow2<72>() || check_pow2<84>() ||
+        check_pow2<4>() || check_pow2<31>() || check_pow2<33>() || check_pow2<63>() || check_pow2<65>() || check_pow2<95>()) return 1;
+    printf("gl_mul_pow2 == gl_mul by 2^T for 13 shifts\n");
     std::vector<u64> twf = make_tw(20, false), twi = make_tw(20, true);
     for (int L = 16; L <= 20; L++) {
         const size_t n = size_t(1) << L;
         N2Pass p1 = {L, 0, 8, 1, 0, L - 8}, p2 = {L, 8, L - 8, 0, 0, 0};
         for (int inv = 0; inv < 2; inv++) {
+            p1.inverse = p2.inverse = inv;
             std::vector<u64> x(n), y(n), ref;
             for (auto &v : x) v = rnd();
             x[0] = GL_P - 1; x[1] = 0; x[n - 1] = GL_P - 1;
@@ -60,6 +70,7 @@ int main() {
             run_pass<2>(p2, y.data(), y.data(), inv ? twi.data() : twf.data(), nullptr, mul);
             for (size_t i = 0; i < n; i++) if (y[bitrev32((u32)i, L)] != gl_mul(ref[i], mul)) { printf("MISMATCH L=%d inv=%d i=%zu\n", L, inv, i); return 1; }
         }
+        p1.inverse = p2.inverse = 0;
         if (L <= 18) {      // coset LDE: coefficients in bit-reversed storage, scale table in the same order
             std::vector<u64> coef(n), stor(n), scale(n), y(n), ref(n);
             for (auto &v : coef) v = rnd();

@@ -105,6 +105,27 @@ GL_HD u64 gl_sub(u64 a, u64 b) {
 }
 GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 
+// x * 2^T mod p for a compile-time 0 < T < 96 with T % 32 != 0, x canonical -> canonical.  2 has order 192 in F_p (2^96 == -1), so
+// the 16th / 64th roots of unity are powers of two and small DFTs need no multiplier: with phi = 2^32 (phi^2 = phi - 1,
+// phi^3 = -1) the shifted value w_lo + w_mid phi + w_hi phi^2 times phi^(T / 32) collapses to two-word sums.
+template <int T> GL_HD u64 gl_mul_pow2(u64 x) {
+    static_assert(T > 0 && T < 96 && (T % 32) != 0, "shift out of range");
+    constexpr int t = T % 32, q = T / 32;
+    const u32 a = (u32)x, b = (u32)(x >> 32);
+    const u32 w_lo = a << t, w_mid = (u32)(x >> (32 - t)), w_hi = b >> (32 - t);
+    if (q == 0) {                   // w_lo + w_mid phi + w_hi (phi - 1)
+        const u64 X = ((u64)w_mid << 32) | w_lo, t1 = ((u64)w_hi << 32) - w_hi;
+        return gl_canon(gl_add_nc1(X, t1));
+    }
+    if (q == 1) {                   // w_lo phi + w_mid (phi - 1) - w_hi
+        const u64 X = (u64)w_lo << 32, t1 = ((u64)w_mid << 32) - w_mid;        // both < p
+        return gl_add(X, gl_sub(t1, (u64)w_hi));
+    }
+    // q == 2:                         w_lo (phi - 1) - (w_mid + w_hi phi)
+    const u64 t1 = ((u64)w_lo << 32) - w_lo, Y = ((u64)w_hi << 32) | w_mid;    // both < p
+    return gl_sub(t1, Y);
+}
+
 GL_HD void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
 #ifdef __CUDA_ARCH__
     // Four INDEPENDENT IMAD.WIDE.U32 and a six-instruction carry chain.  (A chained form -- each product added onto the

@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
     extern __shared__ __align__(128) u64 sm[];
     u64 *IN = sm, *W0 = sm + N2_BUF_WORDS, *W1 = sm + 2 * N2_BUF_WORDS;        // input rows; two work buffers (the bulk store of unit w drains while unit w + 1 computes in the other)
     u64 *twB = sm + 3 * N2_BUF_WORDS;                                          // [16][16] round-table (15 used per row)
-    u64 *twC = twB + 256;                                                      // [16] uniform last-round table (MODE 2)
-    u64 *bar = twC + 16;
+    u64 *bar = twB + 256 + 16;
     const u32 tid = threadIdx.x;
     const N2Pass p = a.p;
     const u64 W = (u64)a.items * a.tiles_per_item;
@@ -100,7 +99,6 @@ __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
     if (MODE == 2) {                                             // contiguous pass: nothing depends on the tile position
         n2_build_twsA<2>(p, a.tw, 0, tid, twsA);
         if (tid < 240) twB[(tid / 15) * 16 + tid % 15] = n2_twB_entry<2>(p, a.tw, 0, tid / 15, tid % 15);
-        if (tid < 15) twC[tid] = n2_twC_entry(a.tw, tid);
         __syncthreads();
     }
 
@@ -122,7 +120,7 @@ __global__ void __launch_bounds__(N2_THREADS, 2) k_ntt2_pass(const N2Args a) {
         n2_first_round<MODE>(p, IN, sc_row, WORK, tid, twsA, twB);     // IN (x coset scale) -> WORK
         __syncthreads();
         if (w + 1 < w1) issue_load(w + 1);                       // IN / SC are free: fetch the next unit behind the remaining rounds
-        if (n2_second_round<MODE>(p, WORK, tid, twB, twC, a.out_mul)) { __syncthreads(); n2_third_round(WORK, tid, twC, a.out_mul); }
+        if (n2_second_round<MODE>(p, WORK, tid, twB, a.out_mul)) { __syncthreads(); n2_third_round(p, WORK, tid, a.out_mul); }
         fence_async_smem();
         __syncthreads();
         bulk_s2g(out_base(item) + n2_row_global(p, pos, tid), WORK + tid * N2_ROW_WORDS, 128);
@@ -161,7 +159,7 @@ void ntt2_dif(const NttTables &T, const u64 *in, size_t in_stride, bool in_bitre
     // pass 1: layers [0, 8) on strided tiles
     N2Args a; memset(&a, 0, sizeof a);
     a.in = in; a.out = out; a.tw = tw; a.scale = scale; a.in_stride = in_stride; a.out_stride = out_stride;
-    a.p.L = L; a.p.l_begin = 0; a.p.B = 8; a.p.strided = 1; a.p.in_bitrev = in_bitrev ? 1 : 0; a.p.logS = L - 8;
+    a.p.L = L; a.p.l_begin = 0; a.p.B = 8; a.p.strided = 1; a.p.in_bitrev = in_bitrev ? 1 : 0; a.p.logS = L - 8; a.p.inverse = inverse ? 1 : 0;
     a.rate_bits = rate_bits; a.out_mul = 1; a.items = (u32)items; a.tiles_per_item = 1u << (L - 12);
     const bool lde_first = in_bitrev;                            // bit-reversed storage in (with or without a coset scale)
     if (!lde_first && rate_bits) throw CudaErr{cudaErrorInvalidValue, __FILE__, __LINE__};

@@ -29,6 +29,7 @@ struct N2Pass {
     int strided;                    // 1: strided pass (B == 8); 0: contiguous last pass
     int in_bitrev;                  // strided first pass of an LDE: input in bit-reversed storage (l_begin == 0)
     int logS;                       // L - l_begin - B  (0 for the contiguous pass)
+    int inverse;                    // inverse transform (twiddle table T.inv): selects the shift table of the multiplier-free last round
 };
 
 GL_HD u32 n2_rev4(u32 x) { return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3); }
@@ -67,6 +68,36 @@ GL_HD void n2_radix(u64 (&x)[1 << R], const u64 *tws) {
         }
     }
 }
+// The round on idx bits [0, 4) of the contiguous pass is a plain 16-point DFT: its twiddles are the 16th roots of unity
+// w_16^k = 2^(156 k) (inverse transform: 2^(36 k)), i.e. shifts (gl_mul_pow2) and sign flips -- 17 shift-multiplies instead
+// of 32 full products per 16 elements.  Same values as n2_radix<4> with the table twiddles tw[2^s + k].
+template <int INV>
+GL_HD void n2_radix16_pow2(u64 (&x)[16]) {
+#pragma unroll
+    for (int s = 3; s >= 0; s--) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if (e & (1 << s)) continue;
+            const int k = e & ((1 << s) - 1);
+            const int E = ((INV ? 36 : 156) * k * (8 >> s)) % 192;          // w_{2^(s+1)}^k = w_16^(k 2^(3-s)) = 2^E
+            const u64 u = x[e], v = x[e | (1 << s)];
+            x[e] = gl_add(u, v);
+            const u64 d = E >= 96 ? gl_sub(v, u) : gl_sub(u, v);
+            u64 r;
+            switch (E % 96) {
+            case 0: r = d; break;
+            case 12: r = gl_mul_pow2<12>(d); break;
+            case 24: r = gl_mul_pow2<24>(d); break;
+            case 36: r = gl_mul_pow2<36>(d); break;
+            case 48: r = gl_mul_pow2<48>(d); break;
+            case 60: r = gl_mul_pow2<60>(d); break;
+            case 72: r = gl_mul_pow2<72>(d); break;
+            default: r = gl_mul_pow2<84>(d); break;
+            }
+            x[e | (1 << s)] = r;
+        }
+    }
+}
 // twiddle-table index of sub-layer s of a round on idx bits [q, q + R) for a group whose elements below bit q read `jbase`
 // (jbase = natural index of the group's first element modulo 2^(P + q), P = logS): tw[2^beta + jbase + k * 2^(P + q)], beta = P + q + s
 GL_HD u64 n2_tw_index(int P, int q, int s, u64 jbase, u32 k) {
@@ -97,13 +128,13 @@ GL_HD void n2_round_gather(const u64 *in, u64 *outb, u32 task, int q, const u64 
 #pragma unroll
     for (int e = 0; e < (1 << R); e++) outb[N2_OFF(base | ((u32)e << q))] = x[e];
 }
-// last round (bits [0, 4)): thread = row; 128-bit accesses
-GL_HD void n2_round_row(const u64 *in, u64 *outb, u32 row, const u64 *tws, u64 out_mul) {
+// last round (bits [0, 4)): thread = row; 128-bit accesses; multiplier-free 16-point DFT
+GL_HD void n2_round_row(const u64 *in, u64 *outb, u32 row, int inverse, u64 out_mul) {
     u64 x[16];
     const u64 *src = in + row * N2_ROW_WORDS;
 #pragma unroll
     for (int e = 0; e < 16; e++) x[e] = src[e];
-    n2_radix<4>(x, tws);
+    if (inverse) n2_radix16_pow2<1>(x); else n2_radix16_pow2<0>(x);
     if (out_mul != 1) {
 #pragma unroll
         for (int e = 0; e < 16; e++) x[e] = gl_mul(x[e], out_mul);
@@ -167,10 +198,6 @@ GL_HD u64 n2_twB_entry(const N2Pass &p, const u64 *tw, u32 pos, u32 c, u32 e) {
     const u64 low0 = ((u64)pos % (S >> 4)) << 4;
     return tw[n2_tw_index(p.logS - 4, 4, s, low0 + c, k)];       // mid bits [0, 4)
 }
-GL_HD u64 n2_twC_entry(const u64 *tw, u32 e) {                    // uniform table of the row round (idx bits [0, 4)), contiguous pass
-    int s = 0; while ((2u << s) <= e + 1) s++;
-    return tw[n2_tw_index(0, 0, s, 0, e + 1 - (1u << s))];
-}
 template <int MODE>
 GL_HD void n2_first_round(const N2Pass &p, const u64 *IN, const u64 *sc_row, u64 *WORK, u32 tid, const u64 (&twsA)[15], const u64 *twB) {
     if (MODE == 1) { n2_round_bitrev_first(IN, sc_row, WORK, tid, twsA); return; }
@@ -190,10 +217,10 @@ GL_HD void n2_first_round(const N2Pass &p, const u64 *IN, const u64 *sc_row, u64
 }
 // second round: in place on WORK.  Returns true if a third round (n2_third_round) follows after a barrier.
 template <int MODE>
-GL_HD bool n2_second_round(const N2Pass &p, u64 *WORK, u32 tid, const u64 *twB, const u64 *twC, u64 out_mul) {
+GL_HD bool n2_second_round(const N2Pass &p, u64 *WORK, u32 tid, const u64 *twB, u64 out_mul) {
     if (MODE != 2) { n2_round_gather<4>(WORK, WORK, tid, 4, twB + (tid & 15) * 16, out_mul); return false; }
     if (p.B > 8) { n2_round_gather<4>(WORK, WORK, tid, 4, twB + (tid & 15) * 16, 1); return true; }
-    n2_round_row(WORK, WORK, tid, twC, out_mul);
+    n2_round_row(WORK, WORK, tid, p.inverse, out_mul);
     return false;
 }
-GL_HD void n2_third_round(u64 *WORK, u32 tid, const u64 *twC, u64 out_mul) { n2_round_row(WORK, WORK, tid, twC, out_mul); }
+GL_HD void n2_third_round(const N2Pass &p, u64 *WORK, u32 tid, u64 out_mul) { n2_round_row(WORK, WORK, tid, p.inverse, out_mul); }
