@@ -9,10 +9,15 @@
 #include "poseidon.cuh"
 
 #define MK_THREADS 128
+#ifdef MK_MINB              /* experiments: force more resident blocks per SM (default: ptxas picks 80 registers = 6 blocks, no spills) */
+#define MK_BOUNDS __launch_bounds__(MK_THREADS, MK_MINB)
+#else
+#define MK_BOUNDS __launch_bounds__(MK_THREADS)
+#endif
 
 // state of thread t lives in shared memory at sm[i * MK_THREADS + t], i < 12
 #define ST(i) sm[(i) * MK_THREADS + threadIdx.x]
-__global__ void __launch_bounds__(MK_THREADS) k_leaves_colmajor(const u64 *__restrict__ data, size_t cols, size_t L, u64 *__restrict__ digests) {
+__global__ void MK_BOUNDS k_leaves_colmajor(const u64 *__restrict__ data, size_t cols, size_t L, u64 *__restrict__ digests) {
     __shared__ u64 sm[12 * MK_THREADS];
     size_t leaf = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const bool active = leaf < L;

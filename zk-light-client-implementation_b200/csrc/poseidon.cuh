@@ -273,6 +273,11 @@ static const pl_c4 h_POSEIDON_L_PK[22] = POSEIDON_L_PK_INIT;
 __constant__ pl_c4 d_POSEIDON_L_RC[96] = POSEIDON_L_RC_INIT;
 __constant__ pl_c4 d_POSEIDON_L_PK[22] = POSEIDON_L_PK_INIT;
 #endif
+#ifndef PL_SBOX_UNROLL
+#define PL_SBOX_UNROLL 2      /* S-boxes interleaved per iteration of the rolled S-box loop of a full round */
+#endif
+#define PL_PRAGMA_(x) _Pragma(#x)
+#define PL_UNROLL(n) PL_PRAGMA_(unroll n)
 #define PL_M21 0x1FFFFFu
 #define PL_M22 0x3FFFFFu
 
@@ -435,7 +440,7 @@ GL_HD void poseidon_permute_limb(u64 *st, const int stride) {
                 const pl_c4 c = rc[i];
                 st[i * stride] = pl_recombine((u32)l0[i] + c.a, (u32)l1[i] + c.b, (u32)l2[i] + c.c);
             }
-#pragma unroll 2
+PL_UNROLL(PL_SBOX_UNROLL)
             for (int i = 0; i < 12; i++) st[i * stride] = poseidon_sbox4(st[i * stride]);
 #pragma unroll
             for (int i = 0; i < 12; i++) pl_split(st[i * stride], l0[i], l1[i], l2[i]);
