@@ -240,10 +240,12 @@ def run_b200(args):
         raise SystemExit("bench: a proof of the headline circuit was rejected by b200_verify (or dev/host proofs differ) -- no number reported")
 
     # ---- one whole BFT-finality block, measured (second half of BASELINE.json's metric; configs[1] at N=1, configs[2] at N=8).
-    # Task graph: b200_plonky2/block_dag.py (reference: prove_bft/bft.rs:38-565).  S: k sig-shaped sub-proofs sharded over the ranks
-    # (host witnesses through b200_prove) -> all-gather of the complete proofs -> C: the k-step recursive chain on rank 0, WHILE
-    # stage A (31 SHA-256-shaped, 9 tiny, 1 stake-shaped leaf proofs) runs on ranks 1..N-1 (N = 1: on a second context of the same
-    # GPU) -> all-gather of the leaf proofs -> F: 55 further recursive aggregations + the PoseidonBN128 wrap on rank 0.
+    # Task graph: b200_plonky2/block_dag.py (the data flow of prove_bft/bft.rs:38-565 + block_finality.rs:200-731).
+    #   S: k sig-shaped sub-proofs sharded over the ranks (host witnesses through b200_prove) -> all-gather of the complete proofs
+    #   C: the k-step recursive chain on rank 0, WHILE stage A runs on ranks 1..N-1 (N = 1: on a second context of the same GPU):
+    #      A1 = independent lanes (7 headers x [4 SHA-256-shaped + 5 recursive], bp_hash, tiny proofs, stake), a gather of the lane
+    #      results among those ranks, A2 = the 15 recursive aggregations that join lanes without touching the signatures
+    #   -> all-gather of stage A's proofs -> F: the 5 folds that consume the signature aggregate + the PoseidonBN128 wrap on rank 0.
     # Wall clock between barriers, max over ranks.
     block = None
     if not args.no_block:
@@ -253,12 +255,14 @@ def run_b200(args):
             rec_cd = wrap_cd = None
             ready = 1
             leaf_ctx = ctx if world > 1 else bp.Context(local)          # N = 1: stage A gets its own context / stream / host thread
-            my_leaf = block_dag.assign_leaf_tasks(world, rank)
+            my_lanes = block_dag.assign_lanes(world, rank)
+            a_ranks, j_rank = block_dag.stage_a_ranks(world), block_dag.join_rank(world)
+            my_joins = block_dag.join_tasks() if rank == j_rank else []
+            sub = dist.new_group(ranks=a_ranks) if (dist and len(a_ranks) > 1) else None      # collective call: every rank makes it
             leaf_cds = {}
             try:
-                for _, kind, db in my_leaf:
-                    if (kind, db) not in leaf_cds:
-                        c_ = workloads.build(kind, db, seed=5); c_.upload(leaf_ctx); c_.prove(leaf_ctx); leaf_cds[(kind, db)] = c_
+                for kind, db in sorted({(kd, d) for _, tasks in my_lanes for _, kd, d in tasks} | {(kd, d) for _, kd, d in my_joins}):
+                    c_ = workloads.build(kind, db, seed=5); c_.upload(leaf_ctx); c_.prove(leaf_ctx); leaf_cds[(kind, db)] = c_
                 if rank == 0:
                     rec_cd = workloads.build("rec", 13, seed=3); rec_cd.upload(ctx)
                     wrap_cd = workloads.build("rec", 12, seed=3, hasher="bn254"); wrap_cd.upload(ctx)
@@ -272,8 +276,10 @@ def run_b200(args):
             mine = sharding.shard_indices(k, world, rank)
             if args.block_streams > 1: pool_ensure(args.block_streams)
             leaf_stride = 200000
-            # warm the proof collective at its real shape (communicator buffers) outside the timed region
+            # warm the proof collectives at their real shapes (communicator buffers) outside the timed region
             sharding.gather_proofs({}, dist, "cuda", (k + world - 1) // world, proof_len[0])
+            if sub is not None and rank in a_ranks:
+                sharding.gather_proofs({}, dist, "cuda", block_dag.max_lane_tasks_per_rank(world), leaf_stride, group=sub, group_size=len(a_ranks))
             barrier(); t0 = time.perf_counter()
             # S
             sig = prove_many(mine, False, args.block_streams, full=True)
@@ -282,44 +288,55 @@ def run_b200(args):
             assert sorted(allsig) == list(range(k))
             t_g1 = time.perf_counter() - t0
             # C (rank 0) || A (ranks 1..N-1, or a second context)
-            leaf_out, errs, t_leaf_busy = {}, [], [0.0]
-            def run_leaves():
+            a_out, errs, t_a_busy, t_a_gather = {}, [], [0.0], [0.0]
+            def run_stage_a():
                 try:
                     ta = time.perf_counter()
-                    for tid_, kind, db in my_leaf: leaf_out[tid_] = leaf_cds[(kind, db)].prove(leaf_ctx)
-                    t_leaf_busy[0] = time.perf_counter() - ta
+                    for _, tasks in my_lanes:                                 # a lane is sequential; lanes are independent
+                        for tid_, kind, db in tasks: a_out[tid_] = leaf_cds[(kind, db)].prove(leaf_ctx)
+                    if sub is not None:                                       # lane results -> the joining rank (and its peers)
+                        tg = time.perf_counter()
+                        lanes_all = sharding.gather_proofs(dict(a_out), dist, "cuda", block_dag.max_lane_tasks_per_rank(world), leaf_stride,
+                                                           group=sub, group_size=len(a_ranks))
+                        assert len(lanes_all) == block_dag.num_lane_tasks()
+                        t_a_gather[0] = time.perf_counter() - tg
+                    for tid_, kind, db in my_joins: a_out[tid_] = leaf_cds[(kind, db)].prove(leaf_ctx)      # A2, in dependency order
+                    t_a_busy[0] = time.perf_counter() - ta
                 except Exception as e: errs.append(e)
-            th = threading.Thread(target=run_leaves); th.start()
+            th = None
+            if rank in a_ranks: th = threading.Thread(target=run_stage_a); th.start()
             t_chain = 0.0
             if rank == 0:
                 tc = time.perf_counter()
                 for i in range(k): rec_cd.prove(ctx, wires=rec_w)            # chain step i consumes sub-proof i (validator order)
                 t_chain = time.perf_counter() - tc
-            th.join()
+            if th is not None: th.join()
             if errs: raise errs[0]
             t_ca = time.perf_counter() - t0
-            allleaf = sharding.gather_proofs(leaf_out, dist, "cuda", block_dag.max_leaf_tasks_per_rank(world), leaf_stride)
-            assert sorted(allleaf) == list(range(len(block_dag.LEAF_SHAPES)))
+            all_a = sharding.gather_proofs(a_out, dist, "cuda", block_dag.max_stage_a_tasks_per_rank(world), leaf_stride)
+            assert sorted(all_a) == list(range(block_dag.num_lane_tasks() + block_dag.JOIN_AGGREGATIONS))
             t_g2 = time.perf_counter() - t0
             # F
             if rank == 0:
-                for _ in range(block_dag.FINAL_AGGREGATIONS): rec_cd.prove(ctx, wires=rec_w)
+                for _ in range(block_dag.POST_CHAIN_FOLDS): rec_cd.prove(ctx, wires=rec_w)
                 wrap_cd.prove(ctx, wires=wrap_w)
             barrier(); t_all = time.perf_counter() - t0
-            tt = torch.tensor([t_sig, t_g1, t_ca, t_g2, t_all, t_chain, t_leaf_busy[0]], dtype=torch.float64, device="cuda")
+            tt = torch.tensor([t_sig, t_g1, t_ca, t_g2, t_all, t_chain, t_a_busy[0], t_a_gather[0]], dtype=torch.float64, device="cuda")
             if dist: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_sig, t_g1, t_ca, t_g2, t_all, t_chain, t_leaf = (float(x) for x in tt.tolist())
+            t_sig, t_g1, t_ca, t_g2, t_all, t_chain, t_leaf, t_ag = (float(x) for x in tt.tolist())
             block = {"bft_block_ms": round(t_all * 1e3, 1), "signature_stage_ms": round(t_sig * 1e3, 1),
                      "subproof_all_gather_ms": round((t_g1 - t_sig) * 1e3, 2),
                      "subproof_all_gather_bytes": sharding.payload_bytes((k + world - 1) // world, proof_len[0], world),
-                     "chain_and_leaf_stage_ms": round((t_ca - t_g1) * 1e3, 1), "chain_ms_rank0": round(t_chain * 1e3, 1),
-                     "leaf_stage_busy_ms_max_rank": round(t_leaf * 1e3, 1), "leaf_all_gather_ms": round((t_g2 - t_ca) * 1e3, 2),
-                     "final_aggregation_and_wrap_ms": round((t_all - t_g2) * 1e3, 1),
+                     "chain_and_stage_a_ms": round((t_ca - t_g1) * 1e3, 1), "chain_ms_rank0": round(t_chain * 1e3, 1),
+                     "stage_a_busy_ms_max_rank": round(t_leaf * 1e3, 1), "stage_a_lane_gather_ms": round(t_ag * 1e3, 2),
+                     "stage_a_all_gather_ms": round((t_g2 - t_ca) * 1e3, 2),
+                     "post_chain_folds_and_wrap_ms": round((t_all - t_g2) * 1e3, 1),
                      "signatures": k, "sig_proofs_per_rank_max": len(sharding.shard_indices(k, world, 0)),
                      "streams_per_gpu_in_signature_stage": args.block_streams, "task_graph": block_dag.summary(k),
-                     "leaf_stage_placement": "ranks 1..N-1 while rank 0 walks the chain" if world > 1 else "second context on the same GPU, concurrent with the chain",
+                     "stage_a_placement": "ranks 1..N-1 while rank 0 walks the chain (joins on rank 1)" if world > 1 else "second context on the same GPU, concurrent with the chain",
                      "note": "measured end to end between barriers (max over ranks): prover time of every proof of the block's task graph with host witnesses; "
-                             "witness generation and circuit builds stay in Rust and are not included; the recursive steps re-prove one recursion-shaped witness"}
+                             "witness generation and circuit builds stay in Rust and are not included; the recursive steps re-prove one recursion-shaped witness; "
+                             "only calls whose inputs never include the signature aggregate run beside the chain, the aggregation tree is the reference's"}
             if rank == 0: rec_cd.free(); wrap_cd.free()
             for c_ in leaf_cds.values(): c_.free()
             if leaf_ctx is not ctx: leaf_ctx.close()

@@ -52,16 +52,18 @@ def pack_proofs(proofs, max_count, stride, device, pin=False):
         t[row, 16:16 + len(b)] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
     return t.to(device, non_blocking=True) if str(device) != "cpu" else t
 
-def gather_proofs(proofs, dist, device, max_count, stride):
-    """ONE all-gather of every rank's packed proofs; returns {index: bytes} of all ranks (identical on every rank)."""
+def gather_proofs(proofs, dist, device, max_count, stride, group=None, group_size=None):
+    """ONE all-gather of every rank's packed proofs; returns {index: bytes} of all ranks (identical on every rank).
+    group / group_size: a torch.distributed sub-group (and its size) for gathers among part of the ranks."""
     import torch
     t = pack_proofs(proofs, max_count, stride, device)
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+    n = group_size if group is not None else (dist.get_world_size() if dist is not None and dist.is_initialized() else 1)
+    if dist is None or not dist.is_initialized() or n == 1:
         allt = t.unsqueeze(0)
     else:
-        allt = torch.empty((dist.get_world_size() * t.shape[0], t.shape[1]), dtype=torch.uint8, device=t.device)
-        dist.all_gather_into_tensor(allt, t)                     # rank r's rows land at [r * max_count, (r + 1) * max_count)
-        allt = allt.view(dist.get_world_size(), t.shape[0], t.shape[1])
+        allt = torch.empty((n * t.shape[0], t.shape[1]), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(allt, t, group=group)        # member r's rows land at [r * max_count, (r + 1) * max_count)
+        allt = allt.view(n, t.shape[0], t.shape[1])
     h = allt.cpu()
     out = {}
     for r in range(h.shape[0]):
