@@ -255,14 +255,17 @@ def run_b200(args):
             rec_cd = wrap_cd = None
             ready = 1
             leaf_ctx = ctx if world > 1 else bp.Context(local)          # N = 1: stage A gets its own context / stream / host thread
+            leaf_ctx2 = None if world > 1 else bp.Context(local)        # ... and a second one: lanes are independent, small proofs are latency-bound
             my_lanes = block_dag.assign_lanes(world, rank)
             a_ranks, j_rank = block_dag.stage_a_ranks(world), block_dag.join_rank(world)
             my_joins = block_dag.join_tasks() if rank == j_rank else []
             sub = dist.new_group(ranks=a_ranks) if (dist and len(a_ranks) > 1) else None      # collective call: every rank makes it
-            leaf_cds = {}
+            leaf_cds, leaf_cds2 = {}, {}
             try:
                 for kind, db in sorted({(kd, d) for _, tasks in my_lanes for _, kd, d in tasks} | {(kd, d) for _, kd, d in my_joins}):
                     c_ = workloads.build(kind, db, seed=5); c_.upload(leaf_ctx); c_.prove(leaf_ctx); leaf_cds[(kind, db)] = c_
+                    if leaf_ctx2 is not None:
+                        c2 = workloads.build(kind, db, seed=5); c2.upload(leaf_ctx2); c2.prove(leaf_ctx2); leaf_cds2[(kind, db)] = c2
                 if rank == 0:
                     rec_cd = workloads.build("rec", 13, seed=3); rec_cd.upload(ctx)
                     wrap_cd = workloads.build("rec", 12, seed=3, hasher="bn254"); wrap_cd.upload(ctx)
@@ -292,8 +295,15 @@ def run_b200(args):
             def run_stage_a():
                 try:
                     ta = time.perf_counter()
-                    for _, tasks in my_lanes:                                 # a lane is sequential; lanes are independent
-                        for tid_, kind, db in tasks: a_out[tid_] = leaf_cds[(kind, db)].prove(leaf_ctx)
+                    def run_lanes(lanes_, cds_, cx_):
+                        try:
+                            for _, tasks in lanes_:                           # a lane is sequential; lanes are independent
+                                for tid_, kind, db in tasks: a_out[tid_] = cds_[(kind, db)].prove(cx_)
+                        except Exception as e: errs.append(e)
+                    if leaf_ctx2 is not None:
+                        t2 = threading.Thread(target=run_lanes, args=(my_lanes[1::2], leaf_cds2, leaf_ctx2)); t2.start()
+                        run_lanes(my_lanes[0::2], leaf_cds, leaf_ctx); t2.join()
+                    else: run_lanes(my_lanes, leaf_cds, leaf_ctx)
                     if sub is not None:                                       # lane results -> the joining rank (and its peers)
                         tg = time.perf_counter()
                         lanes_all = sharding.gather_proofs(dict(a_out), dist, "cuda", block_dag.max_lane_tasks_per_rank(world), leaf_stride,
@@ -333,13 +343,14 @@ def run_b200(args):
                      "post_chain_folds_and_wrap_ms": round((t_all - t_g2) * 1e3, 1),
                      "signatures": k, "sig_proofs_per_rank_max": len(sharding.shard_indices(k, world, 0)),
                      "streams_per_gpu_in_signature_stage": args.block_streams, "task_graph": block_dag.summary(k),
-                     "stage_a_placement": "ranks 1..N-1 while rank 0 walks the chain (joins on rank 1)" if world > 1 else "second context on the same GPU, concurrent with the chain",
+                     "stage_a_placement": "ranks 1..N-1 while rank 0 walks the chain (joins on rank 1)" if world > 1 else "two more contexts on the same GPU (lanes split between them), concurrent with the chain",
                      "note": "measured end to end between barriers (max over ranks): prover time of every proof of the block's task graph with host witnesses; "
                              "witness generation and circuit builds stay in Rust and are not included; the recursive steps re-prove one recursion-shaped witness; "
                              "only calls whose inputs never include the signature aggregate run beside the chain, the aggregation tree is the reference's"}
             if rank == 0: rec_cd.free(); wrap_cd.free()
-            for c_ in leaf_cds.values(): c_.free()
+            for c_ in list(leaf_cds.values()) + list(leaf_cds2.values()): c_.free()
             if leaf_ctx is not ctx: leaf_ctx.close()
+            if leaf_ctx2 is not None: leaf_ctx2.close()
         except Exception as e:
             block = {"bft_block_ms": None, "error": str(e)}
 
@@ -485,7 +496,7 @@ def run_b200(args):
         k = 73
         if all(isinstance(v, float) for v in aux.values()):
             aux["bft_block_estimate_ms"] = round(k * ms_e2e / args.steps + (k + 55) * aux["recursive_proof_2^13_ms"] + aux["bn128_wrap_2^12_ms"], 1)
-            aux["bft_block_estimate_note"] = ("k=73 signed approvals (prove_random fixture): k sig-shaped proofs + (k+55) recursive_proof-shaped proofs + 1 BN128 wrap, "
+            aux["bft_block_estimate_note"] = ("k=73 signed approvals (prove_random fixture): k sig-shaped proofs + (k+55) recursive_proof-shaped proofs + 1 BN128 wrap run one after the other, "
                                               "prover time only (no witness generation / circuit builds, which stay in Rust); SHA-256 sub-proofs not included")
         out_json["aux_proof_shapes"] = aux
     out_json["headline_proof_check"] = {"b200_verify": "accepted on every rank", "dev_bytes_equal_host_bytes": True,
