@@ -306,8 +306,8 @@ def run_b200(args):
                     else: run_lanes(my_lanes, leaf_cds, leaf_ctx)
                     if sub is not None:                                       # lane results -> the joining rank (and its peers)
                         tg = time.perf_counter()
-                        lanes_all = sharding.gather_proofs(dict(a_out), dist, "cuda", block_dag.max_lane_tasks_per_rank(world), leaf_stride,
-                                                           group=sub, group_size=len(a_ranks))
+                        lanes_all = sharding.gather_proofs(dict(a_out), dist, f"cuda:{local}", block_dag.max_lane_tasks_per_rank(world), leaf_stride,
+                                                           group=sub, group_size=len(a_ranks))   # explicit device: torch's current device is per thread
                         assert len(lanes_all) == block_dag.num_lane_tasks()
                         t_a_gather[0] = time.perf_counter() - tg
                     for tid_, kind, db in my_joins: a_out[tid_] = leaf_cds[(kind, db)].prove(leaf_ctx)      # A2, in dependency order
